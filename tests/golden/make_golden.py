@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""Generate golden vectors by running the UNMODIFIED reference (kobanium/TamaGo).
+
+Runs only in the build container (needs /root/reference).  The reference is
+pure Python, has no tests and cannot travel to the GPU box, so everything the
+parity tests need from it is recorded here and committed as small .npz files:
+
+  board_<N>.npz    per-ply board state of random legal games (T0 parity)
+  search_<N>.npz   MCTS trees (sequential halving + PUCT) with a hash
+                   evaluator and counter-based noise injected on both sides (T3)
+  selfplay_9.npz   full self-play games incl. the SGF text (T4)
+  dualnet_<N>.npz  DualNet outputs for seeded numpy weights on real planes (T2)
+  eye_table.npz    the 65 536-entry eye LUT of board/pattern.py
+
+Usage:  python tests/golden/make_golden.py --size 9   (and --size 19)
+        19x19 needs BOARD_SIZE patched in a private copy of the reference; the
+        script makes that copy under /tmp and never writes to /root/reference.
+"""
+import argparse
+import os
+import random
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+
+def prepare_reference(size):
+    src = "/root/reference"
+    if size == 9:
+        return src
+    dst = f"/tmp/tamago_ref{size}"
+    if not os.path.isdir(dst):
+        shutil.copytree(src, dst)
+        os.system(f"chmod -R u+w {dst}")
+        p = os.path.join(dst, "board", "constant.py")
+        s = open(p).read().replace("BOARD_SIZE = 9", f"BOARD_SIZE = {size}")
+        open(p, "w").write(s)
+    return dst
+
+
+def board_state(b, Stone):
+    cells = len(b.board)
+    color = np.array([s.value for s in b.board], np.uint8)
+    libs = np.zeros(cells, np.int16)
+    size = np.zeros(cells, np.int16)
+    for p in range(cells):
+        if b.board[p] in (Stone.BLACK, Stone.WHITE):
+            st = b.strings.string[b.strings.get_id(p)]
+            libs[p] = st.get_num_liberties()
+            size[p] = st.get_size()
+    return color, libs, size
+
+
+def expand_candidates(b, color):
+    """mcts/tree.py:260-264 verbatim call sequence."""
+    cand = b.get_all_legal_pos(color)
+    cand = [c for c in cand if b.check_self_atari_stone(c, color) < 7 and not b.is_complete_eye(c, color)]
+    return cand
+
+
+def gen_board(size, n_games, seed, out):
+    from board.go_board import GoBoard
+    from board.stone import Stone
+    from board.zobrist_hash import hash_bit_mask
+    from nn.feature import generate_input_planes
+    rng = random.Random(seed)
+    rec = {k: [] for k in ("game", "pos", "mover", "color", "libs", "size", "scal", "hash", "legal", "cand",
+                           "satari", "eye", "score", "planes_sum")}
+    planes_samples, planes_keys = [], []
+    for g in range(n_games):
+        b = GoBoard(board_size=size, komi=7.0, check_superko=True)
+        color = Stone.BLACK
+        passes = 0
+        max_plies = min(2 * size * size, 3 * size * size - 4)
+        for ply in range(max_plies):
+            legal = b.get_all_legal_pos(color)
+            cand = expand_candidates(b, color)
+            r = rng.random()
+            # mostly candidate moves, sometimes any legal move (eye fills, self atari), rarely pass
+            if r < 0.03 or not legal:
+                pos = 0
+            elif r < 0.25 or not cand:
+                pos = rng.choice(legal)
+            else:
+                pos = rng.choice(cand)
+            b.put_stone(pos, color)
+            passes = passes + 1 if pos == 0 else 0
+            color = Stone.get_opponent_color(color)
+            c, l, s = board_state(b, Stone)
+            rec["game"].append(g); rec["pos"].append(pos); rec["mover"].append(3 - color.value)
+            rec["color"].append(c); rec["libs"].append(l); rec["size"].append(s)
+            rec["scal"].append([b.moves, b.ko_pos, b.ko_move, b.prisoner[0], b.prisoner[1]])
+            rec["hash"].append(int(b.positional_hash[0]))
+            lg = np.zeros((2, size * size), np.uint8); cd = np.zeros((2, size * size), np.uint8)
+            sa = np.zeros((2, size * size), np.int16); ey = np.zeros((2, size * size), np.uint8)
+            for ci, col in enumerate((Stone.BLACK, Stone.WHITE)):
+                cset = set(expand_candidates(b, col))
+                for i, p in enumerate(b.onboard_pos):
+                    if b.is_legal(p, col):
+                        lg[ci, i] = 1
+                        sa[ci, i] = b.check_self_atari_stone(p, col)
+                        ey[ci, i] = int(b.is_complete_eye(p, col))
+                    cd[ci, i] = int(p in cset)
+            rec["legal"].append(lg); rec["cand"].append(cd); rec["satari"].append(sa); rec["eye"].append(ey)
+            rec["score"].append(b.count_score())
+            pl = generate_input_planes(b, color, 0)
+            w = np.arange(1, pl.size + 1, dtype=np.float64)
+            rec["planes_sum"].append(float((pl.reshape(-1).astype(np.float64) * w).sum()))
+            if rng.random() < 0.02:
+                planes_samples.append(pl); planes_keys.append(len(rec["pos"]) - 1)
+            if passes >= 2 and ply > 20:
+                break
+    np.savez_compressed(
+        out, size=size, zobrist=np.asarray(hash_bit_mask, np.uint64),
+        game=np.array(rec["game"], np.int32), pos=np.array(rec["pos"], np.int16),
+        mover=np.array(rec["mover"], np.uint8), color=np.array(rec["color"], np.uint8),
+        libs=np.array(rec["libs"], np.int16), size_pt=np.array(rec["size"], np.int16),
+        scal=np.array(rec["scal"], np.int32), hash=np.array(rec["hash"], np.uint64),
+        legal=np.packbits(np.array(rec["legal"], np.uint8), axis=-1),
+        cand=np.packbits(np.array(rec["cand"], np.uint8), axis=-1),
+        satari=np.array(rec["satari"], np.int16), eye=np.packbits(np.array(rec["eye"], np.uint8), axis=-1),
+        score=np.array(rec["score"], np.int32), planes_sum=np.array(rec["planes_sum"], np.float64),
+        planes=np.array(planes_samples, np.float32), planes_ply=np.array(planes_keys, np.int32))
+    print(f"board golden: {len(rec['pos'])} plies, {n_games} games -> {out}")
+
+
+class HashNet:
+    """Stands in for DualNet on both sides (oracle.hashnet): exact fp32 outputs."""
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.calls = 0
+
+    def inference(self, x):
+        from oracle.oracle import hashnet
+        pol, val = hashnet(x.numpy(), False)
+        self.calls += x.shape[0]
+        return self.torch.from_numpy(pol), self.torch.from_numpy(val)
+
+    def inference_with_policy_logits(self, x):
+        from oracle.oracle import hashnet
+        pol, val = hashnet(x.numpy(), True)
+        self.calls += x.shape[0]
+        return self.torch.from_numpy(pol), self.torch.from_numpy(val)
+
+
+class NoisePatch:
+    """Replace the reference's np.random draws by the oracle's counter-based noise."""
+    def __init__(self, seed):
+        import mcts.tree as mtree
+        import mcts.node as mnode
+        from oracle import oracle as orc
+        self.seed, self.game, self.move = seed, 0, 0
+        self.tree = None
+        patch = self
+
+        orig_expand = mtree.MCTSTree.expand_node
+
+        def expand_node(tree_self, board, color):
+            patch.node_index = tree_self.num_nodes
+            return orig_expand(tree_self, board, color)
+
+        def tentative(candidates):
+            import ctypes as C
+            k = len(candidates)
+            out = np.zeros(k, np.float64)
+            orc.lib().tgo_dirichlet(patch.seed, patch.game, patch.move, patch.node_index, k,
+                                    out.ctypes.data_as(C.POINTER(C.c_double)))
+            return dict(zip(candidates, out))
+
+        def gumbel(node_self):
+            import ctypes as C
+            out = np.zeros(node_self.noise.size, np.float64)
+            orc.lib().tgo_gumbel(patch.seed, patch.game, patch.move, out.size,
+                                 out.ctypes.data_as(C.POINTER(C.c_double)))
+            node_self.noise = out
+
+        mtree.MCTSTree.expand_node = expand_node
+        mtree.get_tentative_policy = tentative
+        mnode.MCTSNode.set_gumbel_noise = gumbel
+
+    def key(self, game, move):
+        self.game, self.move = game, move
+
+
+def dump_tree(tree):
+    nodes = []
+    for i in range(tree.num_nodes):
+        nd = tree.node[i]
+        k = nd.num_children
+        nodes.append(dict(
+            k=k, node_visits=int(nd.node_visits), virtual_loss=int(nd.virtual_loss),
+            node_value_sum=float(nd.node_value_sum), raw_value=float(nd.raw_value),
+            action=np.array(nd.action[:k], np.int16), cidx=np.array(nd.children_index[:k], np.int32),
+            value=np.array(nd.children_value[:k], np.float64), visits=np.array(nd.children_visits[:k], np.int32),
+            policy=np.array(nd.children_policy[:k], np.float64), vl=np.array(nd.children_virtual_loss[:k], np.int32),
+            vsum=np.array(nd.children_value_sum[:k], np.float64)))
+    return nodes
+
+
+def pack_trees(cases):
+    """Flatten a list of (meta, nodes) into ragged arrays for npz."""
+    out = {}
+    meta_keys = list(cases[0][0].keys())
+    for k in meta_keys:
+        out["case_" + k] = np.array([c[0][k] for c in cases])
+    node_off = [0]
+    child_off = [0]
+    scal, arrs = [], {k: [] for k in ("action", "cidx", "value", "visits", "policy", "vl", "vsum")}
+    for _, nodes in cases:
+        for nd in nodes:
+            scal.append([nd["k"], nd["node_visits"], nd["virtual_loss"]])
+            for k in arrs:
+                arrs[k].append(nd[k])
+            child_off.append(child_off[-1] + nd["k"])
+        node_off.append(node_off[-1] + len(nodes))
+    out["node_off"] = np.array(node_off, np.int64)
+    out["child_off"] = np.array(child_off, np.int64)
+    out["node_scal"] = np.array(scal, np.int32)
+    out["node_fsum"] = np.array([[nd["node_value_sum"], nd["raw_value"]] for _, ns in cases for nd in ns], np.float64)
+    for k, v in arrs.items():
+        out["ch_" + k] = np.concatenate(v) if v else np.zeros(0)
+    return out
+
+
+def positions_for_search(size, seed, count):
+    """A few positions (move lists) reached by random candidate play."""
+    from board.go_board import GoBoard
+    from board.stone import Stone
+    rng = random.Random(seed)
+    plist = [[]]
+    for i in range(count - 1):
+        b = GoBoard(board_size=size, komi=7.0, check_superko=True)
+        color = Stone.BLACK
+        moves = []
+        target = rng.randint(4, size * size + size)
+        for _ in range(target):
+            cand = expand_candidates(b, color)
+            pos = rng.choice(cand) if cand and rng.random() > 0.02 else 0
+            b.put_stone(pos, color)
+            moves.append(pos)
+            color = Stone.get_opponent_color(color)
+        plist.append(moves)
+    return plist
+
+
+def gen_search(size, seed, out, sh_visits, puct_visits):
+    from board.go_board import GoBoard
+    from board.stone import Stone
+    from mcts.tree import MCTSTree
+    from mcts.time_manager import TimeManager, TimeControl
+    net = HashNet()
+    patch = NoisePatch(seed=seed)
+    cases = []
+    movelists = positions_for_search(size, seed + 1, 6 if size == 9 else 3)
+    ml_flat, ml_off = [], [0]
+    for ml in movelists:
+        ml_flat += ml; ml_off.append(len(ml_flat))
+    for pi, ml in enumerate(movelists):
+        b = GoBoard(board_size=size, komi=7.0, check_superko=True)
+        color = Stone.BLACK
+        for p in ml:
+            b.put_stone(p, color); color = Stone.get_opponent_color(color)
+        for visits in sh_visits:
+            tree = MCTSTree(net, tree_size=4096)
+            patch.key(pi, b.moves)
+            tm = TimeManager(TimeControl.CONSTANT_PLAYOUT, constant_visits=visits)
+            mv = tree.generate_move_with_sequential_halving(b, color, tm, True)
+            ip = tree.get_root().calculate_improved_policy()
+            cases.append((dict(kind=0, pos_index=pi, visits=visits, batch=1, move=mv, color=color.value), dump_tree(tree)))
+            cases[-1][1][0]["improved"] = np.asarray(ip, np.float64)
+        for visits, batch in puct_visits:
+            tree = MCTSTree(net, tree_size=4096, batch_size=batch)
+            patch.key(pi, b.moves)
+            tm = TimeManager(TimeControl.CONSTANT_PLAYOUT, constant_visits=visits)
+            mv = tree.search_best_move(b, color, tm, {})
+            cases.append((dict(kind=1, pos_index=pi, visits=visits, batch=batch, move=mv, color=color.value), dump_tree(tree)))
+    packed = pack_trees(cases)
+    improved = [c[1][0].get("improved", np.zeros(0)) for c in cases]
+    packed["improved"] = np.concatenate(improved)
+    packed["improved_off"] = np.cumsum([0] + [len(x) for x in improved])
+    from board.zobrist_hash import hash_bit_mask
+    np.savez_compressed(out, size=size, seed=seed, zobrist=np.asarray(hash_bit_mask, np.uint64),
+                        movelist=np.array(ml_flat, np.int16), movelist_off=np.array(ml_off, np.int64), **packed)
+    print(f"search golden: {len(cases)} cases -> {out}")
+
+
+def gen_selfplay(size, seed, out, visits, n_games):
+    """selfplay/worker.py loop with injected net/noise; keeps the SGF text."""
+    import tempfile
+    from board.go_board import GoBoard, copy_board
+    from board.stone import Stone
+    from board.constant import PASS, RESIGN
+    from mcts.tree import MCTSTree
+    from mcts.time_manager import TimeManager, TimeControl
+    from sgf.selfplay_record import SelfPlayRecord
+    from board.zobrist_hash import hash_bit_mask
+    net = HashNet()
+    patch = NoisePatch(seed=seed)
+    texts, movesl, nres = [], [], []
+    tmp = tempfile.mkdtemp()
+    for g in range(n_games):
+        board = GoBoard(board_size=size, komi=7.0, check_superko=True)
+        record = SelfPlayRecord(tmp, board.coordinate)
+        mcts = MCTSTree(net, tree_size=160)
+        tm = TimeManager(TimeControl.CONSTANT_PLAYOUT, constant_visits=visits)
+        color = Stone.BLACK
+        never_resign = (g % 2 == 0)
+        pass_count, is_resign, score, winner = 0, False, 0.0, Stone.EMPTY
+        moves = []
+        for _ in range(size * size * 2):
+            patch.key(g, board.moves)
+            pos = mcts.generate_move_with_sequential_halving(board=board, color=color, time_manager=tm,
+                                                             never_resign=never_resign)
+            if pos == RESIGN:
+                winner = Stone.get_opponent_color(color); is_resign = True
+                break
+            board.put_stone(pos, color)
+            moves.append(pos)
+            pass_count = pass_count + 1 if pos == PASS else 0
+            record.save_record(mcts.get_root(), pos, color)
+            color = Stone.get_opponent_color(color)
+            if pass_count == 2:
+                winner = Stone.EMPTY
+                break
+        if pass_count == 2:
+            score = board.count_score() - board.get_komi()
+            winner = Stone.BLACK if score > 0.1 else (Stone.WHITE if score < -0.1 else Stone.OUT_OF_BOARD)
+        record.set_index(g)
+        record.write_record(winner, board.get_komi(), is_resign, score)
+        texts.append(open(os.path.join(tmp, f"{g}.sgf"), encoding="utf-8").read())
+        movesl.append(moves); nres.append(int(never_resign))
+        print(f"  selfplay game {g}: {len(moves)} moves, winner {winner}, score {score}")
+    shutil.rmtree(tmp)
+    np.savez_compressed(out, size=size, seed=seed, visits=visits, zobrist=np.asarray(hash_bit_mask, np.uint64),
+                        sgf=np.array(texts), never_resign=np.array(nres),
+                        moves=np.concatenate([np.array(m, np.int16) for m in movesl]),
+                        moves_off=np.cumsum([0] + [len(m) for m in movesl]))
+    print(f"selfplay golden -> {out}")
+
+
+def numpy_weights(size, seed):
+    """Seeded numpy state_dict for DualNet (names: SURVEY.md A.2)."""
+    rs = np.random.RandomState(seed)
+    sd = {}
+
+    def conv(name, o, i, k):
+        sd[name] = (rs.standard_normal((o, i, k, k)) * np.sqrt(2.0 / (i * k * k))).astype(np.float32)
+
+    def bn(prefix, c):
+        sd[prefix + ".weight"] = rs.uniform(0.5, 1.5, c).astype(np.float32)
+        sd[prefix + ".bias"] = (rs.standard_normal(c) * 0.1).astype(np.float32)
+        sd[prefix + ".running_mean"] = (rs.standard_normal(c) * 0.1).astype(np.float32)
+        sd[prefix + ".running_var"] = rs.uniform(0.5, 1.5, c).astype(np.float32)
+        sd[prefix + ".num_batches_tracked"] = np.array(0, np.int64)
+
+    conv("conv_layer.weight", 64, 6, 3); bn("bn_layer", 64)
+    for b in range(6):
+        conv(f"blocks.{b}.conv1.weight", 64, 64, 3); conv(f"blocks.{b}.conv2.weight", 64, 64, 3)
+        bn(f"blocks.{b}.bn1", 64); bn(f"blocks.{b}.bn2", 64)
+    nn_ = size * size
+    conv("policy_head.conv_layer.weight", 2, 64, 1); bn("policy_head.bn_layer", 2)
+    sd["policy_head.fc_layer.weight"] = (rs.standard_normal((nn_ + 1, 2 * nn_)) * np.sqrt(1.0 / (2 * nn_))).astype(np.float32)
+    sd["policy_head.fc_layer.bias"] = (rs.standard_normal(nn_ + 1) * 0.1).astype(np.float32)
+    conv("value_head.conv_layer.weight", 1, 64, 1); bn("value_head.bn_layer", 1)
+    sd["value_head.fc_layer.weight"] = (rs.standard_normal((3, nn_)) * np.sqrt(1.0 / nn_)).astype(np.float32)
+    sd["value_head.fc_layer.bias"] = (rs.standard_normal(3) * 0.1).astype(np.float32)
+    return sd
+
+
+def gen_dualnet(size, seed, board_npz, out):
+    import torch
+    from nn.network.dual_net import DualNet
+    torch.set_grad_enabled(False)
+    net = DualNet(torch.device("cpu"), board_size=size)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in numpy_weights(size, seed).items()}
+    net.load_state_dict(sd)
+    net.eval()
+    planes = np.load(board_npz)["planes"][:24]
+    x = torch.from_numpy(planes)
+    logits, vlogit = net.forward(x)
+    pol_sm, val_sm = net.inference(x)
+    np.savez_compressed(out, size=size, weight_seed=seed, planes=planes, logits=logits.numpy(),
+                        value_logits=vlogit.numpy(), policy_softmax=pol_sm.numpy(), value_softmax=val_sm.numpy())
+    print(f"dualnet golden: {planes.shape[0]} positions -> {out}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=9)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    ref = prepare_reference(a.size)
+    np.random.seed(20261017)          # BEFORE importing board.* (Zobrist table is drawn at import)
+    random.seed(20261017)
+    sys.path.insert(0, ref)
+    import torch
+    torch.manual_seed(0)
+    N = a.size
+    want = lambda k: (not a.only) or k in a.only.split(",")
+    if want("eye") and N == 9:
+        from board.go_board import GoBoard
+        b = GoBoard(board_size=9)
+        eye = np.array([s.value for s in b.pattern.eye], np.uint8)
+        np.savez_compressed(os.path.join(HERE, "eye_table.npz"), eye=eye)
+    if want("board"):
+        gen_board(N, 24 if N == 9 else 3, 1234, os.path.join(HERE, f"board_{N}.npz"))
+    if want("search"):
+        if N == 9:
+            gen_search(N, 77, os.path.join(HERE, f"search_{N}.npz"), [16, 50, 400], [(100, 1), (120, 8)])
+        else:
+            gen_search(N, 77, os.path.join(HERE, f"search_{N}.npz"), [50], [(40, 1)])
+    if want("selfplay") and N == 9:
+        gen_selfplay(N, 5, os.path.join(HERE, "selfplay_9.npz"), visits=16, n_games=3)
+    if want("dualnet"):
+        gen_dualnet(N, 31337, os.path.join(HERE, f"board_{N}.npz"), os.path.join(HERE, f"dualnet_{N}.npz"))
+
+
+if __name__ == "__main__":
+    main()
