@@ -1,0 +1,162 @@
+/*
+ * tamago_b200.h -- C ABI of the B200-native TamaGo self-play / search engine.
+ *
+ * The reference (kobanium/TamaGo) is pure Python and has no FFI; its seams for this path are Python
+ * classes.  Each entry point below names the reference interface it stands in for (file:line relative to
+ * the reference checkout).  A maintainer binds the library with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative tg_status, and
+ *     tg_last_error() gives the message of the last failure on the calling thread;
+ *   - one engine = one GPU = one host thread at a time; work is queued on the engine's CUDA stream and the
+ *     functions that return data to host buffers synchronise before returning;
+ *   - positions are the reference's padded indices pos = x + y*(N+2), x,y in [1,N]; PASS = 0, RESIGN = -1
+ *     (board/constant.py:24-26); colours are Stone values 1 = black, 2 = white (board/stone.py:5);
+ *   - per-child arrays have the stride tg_action_stride(N) (= N*N+1 rounded up to 32).
+ */
+#ifndef TAMAGO_B200_H
+#define TAMAGO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tg_engine tg_engine;
+
+enum tg_status { TG_OK = 0, TG_ERR_ARG = -1, TG_ERR_CUDA = -2, TG_ERR_STATE = -3, TG_ERR_SEARCH = -4 };
+enum tg_mode { TG_MODE_SH = 0,      /* Gumbel sequential halving: MCTSTree.generate_move_with_sequential_halving, mcts/tree.py:318 */
+               TG_MODE_PUCT = 1 };  /* PUCT: MCTSTree.search_best_move, mcts/tree.py:57 */
+enum tg_evaluator { TG_EVAL_DUALNET_TC = 0,   /* tcgen05 tensor-core DualNet (product path) */
+                    TG_EVAL_DUALNET_FP32 = 1, /* CUDA-core fp32 DualNet (on-device numerical reference) */
+                    TG_EVAL_HASHNET = 2 };    /* deterministic hash evaluator with exact fp32 outputs (tree parity tests) */
+
+typedef struct tg_config {
+    int32_t board_size;       /* N: 9, 13 or 19 (board/constant.py:4 BOARD_SIZE) */
+    float   komi;             /* GoBoard(komi=...), board/go_board.py:20 */
+    int32_t superko;          /* GoBoard(check_superko=...) */
+    int32_t games;            /* concurrent games (board + tree pools) on this GPU */
+    int32_t max_visits;       /* largest visit budget that will be requested (sizes the node pool and leaf queue) */
+    int32_t batch_size;       /* PUCT leaves per game per evaluation: MCTSTree(batch_size=...), mcts/tree.py:29 */
+    int32_t max_nodes;        /* nodes per game; 0 = max_visits + 2 (MCTSTree(tree_size=...)) */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t evaluator;        /* tg_evaluator */
+    int32_t dedup;            /* 1: evaluate identical leaves of one batch once (result-preserving) */
+    int32_t cgos_mode;        /* MCTSTree(cgos_mode=...) */
+    int32_t net_blocks;       /* DualNet residual blocks (nn/network/dual_net.py:26), default 6 */
+    uint64_t seed;            /* seed of the counter-based Dirichlet/Gumbel stream */
+} tg_config;
+
+/* DualNet parameters: host fp32 arrays named as in DualNet.state_dict() (nn/network/dual_net.py:14-39).
+ * bn arrays are [4][C]: weight, bias, running_mean, running_var. */
+typedef struct tg_weights {
+    const float* conv_w;            /* conv_layer.weight        [64][6][3][3]  */
+    const float* bn;                /* bn_layer.*               [4][64]        */
+    float        bn_eps;            /* 1e-5 (dual_net.py:32)                   */
+    const float* block_conv_w;      /* blocks.i.conv{1,2}.weight [blocks][2][64][64][3][3] */
+    const float* block_bn;          /* blocks.i.bn{1,2}.*        [blocks][2][4][64]        */
+    float        block_bn_eps;      /* 2e-5 (res_block.py:23-24)               */
+    const float* policy_conv_w;     /* policy_head.conv_layer.weight [2][64]   */
+    const float* policy_bn;         /* policy_head.bn_layer.*   [4][2]         */
+    const float* policy_fc_w;       /* policy_head.fc_layer.weight [N*N+1][2*N*N] */
+    const float* policy_fc_b;       /* policy_head.fc_layer.bias [N*N+1]       */
+    const float* value_conv_w;      /* value_head.conv_layer.weight [1][64]    */
+    const float* value_bn;          /* value_head.bn_layer.*    [4][1]         */
+    const float* value_fc_w;        /* value_head.fc_layer.weight [3][N*N]     */
+    const float* value_fc_b;        /* value_head.fc_layer.bias [3]            */
+    float        head_bn_eps;       /* 2e-5 (head/policy_head.py:21, head/value_head.py:22) */
+} tg_weights;
+
+/* Per-ply state dump of tg_play (parity tests): what GoBoard / StringData expose after put_stone. */
+typedef struct tg_ply_dump {
+    uint8_t*  color;    /* [games][plies][(N+2)^2]  GoBoard.board                               */
+    int16_t*  libs;     /* [games][plies][(N+2)^2]  String.get_num_liberties() of the stone's string */
+    int16_t*  size;     /* [games][plies][(N+2)^2]  String.get_size()                            */
+    int32_t*  scal;     /* [games][plies][5]        moves, ko_pos, ko_move, prisoner[0], prisoner[1] */
+    uint64_t* hash;     /* [games][plies]           positional_hash                              */
+    uint8_t*  legal;    /* [games][plies][2][N*N]   is_legal for black, white (go_board.py:260)  */
+    int16_t*  satari;   /* [games][plies][2][N*N]   check_self_atari_stone (go_board.py:327), 0 where illegal */
+    uint8_t*  eye;      /* [games][plies][2][N*N]   is_complete_eye (go_board.py:367), 0 where illegal */
+    uint8_t*  cand;     /* [games][plies][2][N*N]   expansion candidates (mcts/tree.py:260-263)  */
+    int32_t*  score;    /* [games][plies]           count_score (go_board.py:561)                */
+    int32_t   plies;    /* plies allocated per game */
+} tg_ply_dump;
+
+/* Result of one move of every game (host buffers, caller-owned; any pointer may be NULL). */
+typedef struct tg_step_result {
+    int32_t* move;          /* [games] chosen pos, PASS 0, RESIGN -1, -2 = slot idle                      */
+    int32_t* color;         /* [games] colour that moved                                                   */
+    int32_t* num_children;  /* [games] root.get_num_children()                                             */
+    int16_t* action;        /* [games][stride] root.action (sgf/selfplay_record.py:56-61)                  */
+    double*  improved;      /* [games][stride] root.calculate_improved_policy() (mcts/node.py:308)         */
+    int32_t* visits;        /* [games][stride] root.children_visits                                        */
+    int32_t* finished;      /* [games] 1 when the game ended with this move                                */
+    int32_t* winner;        /* [games] Stone value: 1, 2, 3 = draw (OUT_OF_BOARD), 0 = undecided (worker.py:57-87) */
+    int32_t* resigned;      /* [games]                                                                     */
+    float*   score;         /* [games] count_score() - komi (worker.py:81)                                 */
+    int32_t* error;         /* [games] search error bits (0 = ok)                                          */
+    int64_t* evals;         /* [1] network evaluations executed by this call                               */
+} tg_step_result;
+
+/* One node of a game's tree (MCTSNode, mcts/node.py:18-39), for tree-parity tests and get_root(). */
+typedef struct tg_node_view {
+    int32_t num_children, node_visits, virtual_loss;
+    float   node_value_sum, raw_value;
+    int16_t* action;            /* [stride] */
+    int32_t* children_index;    /* [stride] */
+    float*   children_value;    /* [stride] */
+    int32_t* children_visits;   /* [stride] */
+    double*  children_policy;   /* [stride] */
+    int32_t* children_virtual_loss; /* [stride] */
+    float*   children_value_sum;    /* [stride] */
+    double*  noise;             /* [stride] root noise of the game (only filled for node 0) */
+} tg_node_view;
+
+const char* tg_last_error(void);
+int  tg_action_stride(int board_size);
+
+/* GoBoard pool + MCTSTree pool + DualNet on one GPU. */
+int  tg_engine_create(const tg_config* cfg, tg_engine** out);
+void tg_engine_destroy(tg_engine* e);
+
+/* board/zobrist_hash.py:9-10 hash_bit_mask [4][(N+2)^2] (drawn unseeded at import by the reference, hence an input) */
+int  tg_set_zobrist(tg_engine* e, const uint64_t* table);
+/* nn/utility.py:139-159 load_network: parameters of DualNet */
+int  tg_load_weights(tg_engine* e, const tg_weights* w);
+
+/* GoBoard.clear (go_board.py:111) for the games flagged in mask (NULL = all); game_ids key the noise stream */
+int  tg_reset(tg_engine* e, const uint8_t* mask, const uint64_t* game_ids, const uint8_t* never_resign);
+/* GoBoard.put_stone (go_board.py:131) for counts[g] moves of every game; colors NULL = alternate from the side to move */
+int  tg_play(tg_engine* e, const int16_t* moves, const uint8_t* colors, const int32_t* counts, int32_t stride, tg_ply_dump* dump);
+/* side to move of every game (the colour passed to the search) */
+int  tg_set_to_move(tg_engine* e, const int32_t* colors);
+
+/* nn/feature.py:10 generate_input_planes(board, color, sym=0) of every root position -> [games][6][N][N] fp32 */
+int  tg_planes(tg_engine* e, float* out);
+/* DualNet.inference / inference_with_policy_logits (dual_net.py:81-106): planes [n][6][N][N] -> policy [n][N*N+1], value [n][3] */
+int  tg_forward(tg_engine* e, const float* planes, int32_t n, int32_t use_logit, float* policy, float* value);
+
+/* MCTSTree.generate_move_with_sequential_halving (tree.py:318) / search_best_move (tree.py:57) for every game.
+ * play = 1 additionally runs the body of selfplay_worker's move loop (worker.py:58-87). */
+int  tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t strict, int32_t play, tg_step_result* out);
+
+/* MCTSTree.node[index] of one game */
+int  tg_tree_size(tg_engine* e, int32_t game, int32_t* num_nodes);
+int  tg_read_node(tg_engine* e, int32_t game, int32_t index, tg_node_view* out);
+
+/* sgf/selfplay_record.py:67-110 write_record: SGF text of one finished game from the per-move records.
+ * Returns the number of bytes written (excluding the terminator) or a negative status. */
+int  tg_format_sgf(int32_t board_size, int32_t n_moves, const int32_t* moves, const int32_t* colors,
+                   const int32_t* num_children, const int16_t* action, const double* improved, int32_t stride,
+                   int32_t winner, int32_t resigned, double score, double komi, char* out, int32_t out_cap);
+
+/* instrumentation: kernels launched by this engine so far, and device milliseconds of the last tg_genmove */
+int64_t tg_launch_count(tg_engine* e);
+float   tg_last_device_ms(tg_engine* e);
+/* device pointers of the evaluator batch (planes in, policy/value out) for benchmarks that time single kernels */
+int  tg_bench_kernel(tg_engine* e, const char* name, int32_t slots, int32_t iters, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

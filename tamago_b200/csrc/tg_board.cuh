@@ -19,13 +19,18 @@ namespace tg {
 
 template <int N> struct WBoard {
     using G = Geo<N>;
-    u64      cx[G::CP];        // by label: XOR of mover-opponent Zobrist keys of the string (super-ko), analysis only
     unsigned ls[G::CP];        // by label: liberties << 16 | size
-    unsigned lmin[G::CP];      // by label: smallest liberty position          (analysis only)
-    unsigned lmax[G::CP];      // by label: largest liberty position           (analysis only)
     unsigned bloom[BLOOM_WORDS];
     uint16_t chain[G::CP];     // label of the string owning a stone
     uint8_t  color[G::CP];
+};
+
+// Scratch for the expansion-time analysis of one board (one per warp).
+template <int N> struct WAnalysis {
+    using G = Geo<N>;
+    u64      cx[G::CP];        // by label: XOR of mover-opponent Zobrist keys of the string (super-ko)
+    unsigned lmin[G::CP];      // by label: smallest liberty position
+    unsigned lmax[G::CP];      // by label: largest liberty position
 };
 
 struct BScal {                 // replicated across the warp
@@ -236,10 +241,10 @@ template <int N> __device__ __forceinline__ unsigned pat3_at(const WBoard<N>& b,
 
 // per-string liberty extremes and (for super-ko) string key XORs; call before wb_point_status
 template <int N>
-__device__ inline void wb_prepare_analysis(WBoard<N>& b, int mover, bool superko, const u64* __restrict__ zob, int lane)
+__device__ inline void wb_prepare_analysis(const WBoard<N>& b, WAnalysis<N>& an, int mover, bool superko, const u64* __restrict__ zob, int lane)
 {
     using G = Geo<N>;
-    for (int c = lane; c < G::CP; c += 32) { b.lmin[c] = 0xffffu; b.lmax[c] = 0; b.cx[c] = 0; }
+    for (int c = lane; c < G::CP; c += 32) { an.lmin[c] = 0xffffu; an.lmax[c] = 0; an.cx[c] = 0; }
     __syncwarp();
     const int other = opp(mover);
     for (int c = lane; c < G::CELLS; c += 32) {
@@ -249,11 +254,11 @@ __device__ inline void wb_prepare_analysis(WBoard<N>& b, int mover, bool superko
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int cc = b.color[q[i]];
-                if (cc == BLACK || cc == WHITE) { const int l = b.chain[q[i]]; atomicMin(&b.lmin[l], (unsigned)c); atomicMax(&b.lmax[l], (unsigned)c); }
+                if (cc == BLACK || cc == WHITE) { const int l = b.chain[q[i]]; atomicMin(&an.lmin[l], (unsigned)c); atomicMax(&an.lmax[l], (unsigned)c); }
             }
         } else if (superko && (col == BLACK || col == WHITE)) {
             const int l = b.chain[c];
-            if ((b.ls[l] >> 16) == 1u) atomicXor(&b.cx[l], zob[other * G::CELLS + c]);   // go_board.py:290-292: always the opponent's keys
+            if ((b.ls[l] >> 16) == 1u) atomicXor(&an.cx[l], zob[other * G::CELLS + c]);   // go_board.py:290-292: always the opponent's keys
         }
     }
     __syncwarp();
@@ -263,7 +268,7 @@ struct PointStatus { bool legal_pre; bool need_scan; u64 h; int satari; bool eye
 
 // Lane-local part of is_legal / check_self_atari_stone / is_complete_eye for one point.
 template <int N>
-__device__ inline PointStatus wb_point_status(const WBoard<N>& b, const BScal& s, int pos, int color, bool superko,
+__device__ inline PointStatus wb_point_status(const WBoard<N>& b, const WAnalysis<N>& an, const BScal& s, int pos, int color, bool superko,
                                               const u64* __restrict__ zob, const uint8_t* __restrict__ eye_lut)
 {
     using G = Geo<N>;
@@ -294,7 +299,7 @@ __device__ inline PointStatus wb_point_status(const WBoard<N>& b, const BScal& s
             if (nl[i] < 0 || nlibs[i] != 1) continue;
             bool dup = false;
             for (int k = 0; k < i; k++) dup |= (nl[k] == nl[i]);
-            if (!dup) h ^= b.cx[nl[i]];
+            if (!dup) h ^= an.cx[nl[i]];
         }
         r.h = h;
         if (h == 0) r.legal_pre = false;            // record.py:63 also matches the unused (zero) slots
@@ -316,7 +321,7 @@ __device__ inline PointStatus wb_point_status(const WBoard<N>& b, const BScal& s
                 for (int k = 0; k < i; k++) dup |= (ncol[k] == color && nl[k] == nl[i]);
                 if (dup) continue;
                 if (nlibs[i] >= 3) { zero = true; continue; }
-                const int a = (int)b.lmin[nl[i]], c2 = (int)b.lmax[nl[i]];
+                const int a = (int)an.lmin[nl[i]], c2 = (int)an.lmax[nl[i]];
                 bool da = false, dc = false;
                 for (int k = 0; k < nlib; k++) { da |= (lib[k] == a); dc |= (lib[k] == c2); }
                 if (!da) lib[nlib++] = a;
@@ -362,16 +367,16 @@ __device__ inline bool wb_hash_in_history(u64 h, const u64* hist_hash, int moves
 // resolved for the block, every lane calls block_done(base, idx, pos, legal, satari, eye) for its own point
 // (idx = base + lane; idx >= N*N lanes pass legal = false), so the callback may use warp ballots.
 template <int N, class BlockFn>
-__device__ inline void wb_analyze(WBoard<N>& b, const BScal& s, int color, bool superko, const u64* __restrict__ zob,
+__device__ inline void wb_analyze(const WBoard<N>& b, WAnalysis<N>& an, const BScal& s, int color, bool superko, const u64* __restrict__ zob,
                                   const uint8_t* __restrict__ eye_lut, const u64* hist_hash, int lane, BlockFn&& block_done)
 {
     using G = Geo<N>;
-    wb_prepare_analysis(b, color, superko, zob, lane);
+    wb_prepare_analysis(b, an, color, superko, zob, lane);
     for (int base = 0; base < G::NN; base += 32) {
         const int idx = base + lane;
         PointStatus st; st.legal_pre = false; st.need_scan = false; st.h = 0; st.satari = 0; st.eye = false;
         int pos = 0;
-        if (idx < G::NN) { pos = onboard_pos<N>(idx); st = wb_point_status(b, s, pos, color, superko, zob, eye_lut); }
+        if (idx < G::NN) { pos = onboard_pos<N>(idx); st = wb_point_status(b, an, s, pos, color, superko, zob, eye_lut); }
         bool legal = st.legal_pre;
         unsigned m = __ballot_sync(0xffffffffu, legal && st.need_scan);
         while (m) {
@@ -384,25 +389,39 @@ __device__ inline void wb_analyze(WBoard<N>& b, const BScal& s, int color, bool 
     }
 }
 
-// nn/feature.py:10-57 (sym 0): six fp32 planes of the position for the side to move.
+// Leaf snapshot: everything nn/feature.py:10-57 reads from a board, packed for the feature-plane kernel.
+//   bytes [0,2) previous move as raster index (-1: none or pass), [2] previous move was a pass,
+//   [3] colour to move, [4,16) reserved, [16,16+NN) stone colours in raster order.
+template <int N> struct Snap {
+    static constexpr int HDR = 16;
+    static constexpr int BYTES = (HDR + Geo<N>::NN + 15) & ~15;
+};
 template <int N>
-__device__ inline void wb_planes(const WBoard<N>& b, const BScal& s, int color, const int16_t* hist_pos, float* out, int lane)
+__device__ inline void wb_snapshot(const WBoard<N>& b, const BScal& s, int color, const int16_t* hist_pos, uint8_t* out, int lane)
 {
     using G = Geo<N>;
     const int prev = (s.moves - 1 < G::MAXREC) ? hist_pos[s.moves - 1] : 0;   // record.get(moves-1); slot 0 = PASS
-    const bool prev_pass = (s.moves > 1 && prev == PASS);
-    const float cval = (color == WHITE) ? -1.0f : 1.0f;
-    for (int idx = lane; idx < G::NN; idx += 32) {
-        const int pos = onboard_pos<N>(idx);
-        int d = b.color[pos];
-        if (color == WHITE && d != 0) d = 3 - d;                                // :24-25
-        out[0 * G::NN + idx] = d == 0 ? 1.0f : 0.0f;
-        out[1 * G::NN + idx] = d == 1 ? 1.0f : 0.0f;
-        out[2 * G::NN + idx] = d == 2 ? 1.0f : 0.0f;
-        out[3 * G::NN + idx] = (!prev_pass && prev == pos) ? 1.0f : 0.0f;      // :43-46
-        out[4 * G::NN + idx] = prev_pass ? 1.0f : 0.0f;                         // :39-41
-        out[5 * G::NN + idx] = cval;                                            // :50-52
+    const bool prev_pass = (s.moves > 1 && prev == PASS);                      // feature.py:39-41
+    if (lane == 0) {
+        const int pidx = (prev == PASS) ? -1 : ((prev % G::W) - 1) + ((prev / G::W) - 1) * N;
+        *reinterpret_cast<int16_t*>(out) = (int16_t)pidx;
+        out[2] = prev_pass ? 1 : 0;
+        out[3] = (uint8_t)color;
     }
+    for (int idx = lane; idx < G::NN; idx += 32) out[Snap<N>::HDR + idx] = b.color[onboard_pos<N>(idx)];
+}
+
+// nn/feature.py:10-57 (sym 0): value of plane p at raster index idx for a snapshot.
+template <int N>
+__device__ __forceinline__ float snap_plane_value(const uint8_t* snap, int p, int idx)
+{
+    const int color = snap[3];
+    if (p == 5) return color == WHITE ? -1.0f : 1.0f;                           // :50-52
+    if (p == 4) return snap[2] ? 1.0f : 0.0f;                                   // :39-41
+    if (p == 3) return (*reinterpret_cast<const int16_t*>(snap) == idx) ? 1.0f : 0.0f;   // :43-46
+    int d = snap[Snap<N>::HDR + idx];
+    if (color == WHITE && d != 0) d = 3 - d;                                    // :24-25
+    return d == p ? 1.0f : 0.0f;                                                // :31
 }
 
 // GoBoard.count_score (go_board.py:561-608) with its raster-order, non-flood-fill colouring.

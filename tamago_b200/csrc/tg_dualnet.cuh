@@ -1,0 +1,535 @@
+// tg_dualnet.cuh -- DualNet forward pass (nn/network/dual_net.py:41-106, res_block.py:27-39,
+// policy_head.py:25-40, value_head.py:26-40) for sm_100a.
+//
+// k_dualnet_tc: the whole network for a group of boards in ONE persistent CTA per SM.
+//   * every 3x3 convolution is an implicit GEMM on the 5th-gen tensor cores: tcgen05.mma (kind::f16,
+//     M=128 board points x N=64 output channels x K=16 input channels per instruction), accumulators in TMEM;
+//   * activations never leave the SM: they sit in shared memory as fp16 (hi, lo) pairs in the no-swizzle
+//     K-major "interleaved" layout [8-channel chunk][row][8 ch], where a row is one point of the flattened,
+//     halo-padded boards.  A 3x3 tap is then nothing but a row shift of the operand's start address, so the nine
+//     taps are nine shared-memory descriptors over the same buffer (no im2col, no copies);
+//   * fp32-grade accuracy from fp16 operands: x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, three MMAs accumulating
+//     into the same fp32 TMEM tile (error ~2^-22 per product; the reference net is fp32, tolerance 1e-4);
+//   * BatchNorm (eval mode) is folded into the weights/bias on the host; the residual skip never touches
+//     memory: the block input is parked in a second TMEM region and conv2 accumulates on top of it;
+//   * weights (16 KB per tap: hi+lo) stream from L2 through a 4-stage cp.async.bulk/mbarrier ring;
+//   * warp roles: 0 = weight producer, 1 = MMA issuer, 2..9 = epilogue (TMEM -> bias/ReLU/split -> smem) and heads.
+//
+// k_conv3x3_simt / k_heads_simt: plain fp32 CUDA-core implementation of the same network, used as the on-device
+// numerical reference for the tensor-core kernel and for board sizes without a tensor-core instantiation.
+#pragma once
+#include <cuda_fp16.h>
+#include "tg_common.cuh"
+
+namespace tg {
+
+constexpr int NET_F = 64;                 // filters (dual_net.py:25)
+constexpr int W_STAGES = 4;
+constexpr int W_STAGE_BYTES = 2 * 8 * 64 * 16;      // hi+lo, 8 chunks x 64 oc x 16 B = 16 KB
+
+struct NetDev {
+    int blocks;                  // residual blocks (dual_net.py:26)
+    // tensor-core operands
+    const __half* w_stem;        // [9 taps][2 terms][2 chunks][64 oc][8 ic]
+    const __half* w_conv;        // [2*blocks][9 taps][2 terms][8 chunks][64 oc][8 ic]
+    const float* bias;           // [1+2*blocks][64]   BN-folded bias
+    const float* scale;          // [1+2*blocks]       power-of-two weight scale of the layer
+    // heads (fp32)
+    const float* head_w;         // [3][64]  policy conv (2) + value conv (1), BN folded
+    const float* head_b;         // [3]
+    const float* pfc_t;          // [2*NN][A]  policy FC, transposed
+    const float* pfc_b;          // [A]
+    const float* vfc_w;          // [3][NN]
+    const float* vfc_b;          // [3]
+    // fp32 CUDA-core path
+    const float* w32_stem;       // [6 ic][9][64 oc]
+    const float* w32_conv;       // [2*blocks][64 ic][9][64 oc]
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{ asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// no-swizzle K-major operand: rows 16 B apart inside an 8-row core matrix, SBO between 8-row groups,
+// LBO between the two 8-element K chunks of one K=16 step (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16)
+         | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D=F32, A=B=F16, both K-major, M=128, N=64 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC_F16_M128_N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+#define TG_TMEM_LD32(taddr, v) \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
+        : "r"(taddr) : "memory")
+#define TG_TMEM_ST32(taddr, v) \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], " \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};" \
+        :: "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
+           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), \
+           "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), \
+           "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]), \
+           "r"(taddr) : "memory")
+
+// ------------------------------------------------------------------------------------------------
+// Geometry of the flattened, halo-padded board group held by one CTA.
+//   point (y, x) of board b  ->  row  b*BR + PITCH + y*PITCH + x      (PITCH = N+1: one shared halo column,
+//   one shared halo line between consecutive boards); tap (dy, dx) = row shift dy*PITCH + dx.
+// ------------------------------------------------------------------------------------------------
+template <int N, int G> struct NetGeo {
+    static constexpr int NN = N * N, A = NN + 1;
+    static constexpr int PITCH = N + 1;
+    static constexpr int BR = PITCH * PITCH;                    // rows per board
+    static constexpr int MROWS = G * BR;
+    static constexpr int TILES = (MROWS + 127) / 128;
+    static constexpr int L0 = ((PITCH + 1 + 7) / 8) * 8;         // leading zero rows
+    static constexpr int R = ((L0 + TILES * 128 + PITCH + 1 + 7) / 8) * 8;   // rows allocated per chunk plane
+    static constexpr int PLANE_BYTES = R * 16;                   // one 8-channel chunk plane
+    static constexpr int ACT_BYTES = 8 * PLANE_BYTES;            // one fp16 copy (hi or lo) of the activations
+    static constexpr int COL_S = 0, COL_A = 256;                 // TMEM regions: S (skip / stem / conv2), A (conv1)
+    static_assert(TILES * 64 <= 256, "group too large for the two TMEM regions");
+    // shared memory carve-up
+    static constexpr int OFF_HI = 0;
+    static constexpr int OFF_LO = OFF_HI + ACT_BYTES;
+    static constexpr int OFF_W = OFF_LO + ACT_BYTES;
+    static constexpr int OFF_BIAS = OFF_W + W_STAGES * W_STAGE_BYTES;          // [32 layers][64] fp32
+    static constexpr int OFF_HEADW = OFF_BIAS + 32 * 64 * 4;                   // [3][64] + [4]
+    static constexpr int OFF_PACT = OFF_HEADW + (3 * 64 + 4) * 4;              // [G][2*NN] policy-head activations
+    static constexpr int OFF_VACT = OFF_PACT + G * 2 * NN * 4;                 // [G][NN]
+    static constexpr int OFF_LOGIT = OFF_VACT + G * NN * 4;                    // [G][A]
+    static constexpr int OFF_BAR = (OFF_LOGIT + G * A * 4 + 15) & ~15;         // mbarriers + tmem address
+    static constexpr int SMEM_BYTES = OFF_BAR + 128;
+};
+
+constexpr int TC_THREADS = 320;           // 10 warps
+constexpr int EPI_THREADS = 256;
+
+template <int N, int G>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__ n_slots_ptr, int use_logit,
+             float* __restrict__ policy, float* __restrict__ value)
+{
+    using NG = NetGeo<N, G>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_slots = *n_slots_ptr;
+    const int ngroups = (n_slots + G - 1) / G;
+    const int L = 1 + 2 * P.blocks;
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NG::OFF_BAR);
+    const uint32_t bar_wfull = smem_u32(bars + 0);           // [W_STAGES]
+    const uint32_t bar_wempty = smem_u32(bars + W_STAGES);   // [W_STAGES]
+    const uint32_t bar_accfull = smem_u32(bars + 2 * W_STAGES);
+    const uint32_t bar_actready = smem_u32(bars + 2 * W_STAGES + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * W_STAGES + 2);
+
+    // ---- one-time setup -------------------------------------------------------------------------
+    {   // zero both activation copies once (halo rows stay zero for the lifetime of the CTA)
+        uint4* z = reinterpret_cast<uint4*>(smem + NG::OFF_HI);
+        for (int i = threadIdx.x; i < 2 * NG::ACT_BYTES / 16; i += TC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        float* bs = reinterpret_cast<float*>(smem + NG::OFF_BIAS);
+        for (int i = threadIdx.x; i < L * 64; i += TC_THREADS) bs[i] = P.bias[i];
+        float* hw = reinterpret_cast<float*>(smem + NG::OFF_HEADW);
+        for (int i = threadIdx.x; i < 3 * 64; i += TC_THREADS) hw[i] = P.head_w[i];
+        if (threadIdx.x < 3) hw[3 * 64 + threadIdx.x] = P.head_b[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < W_STAGES; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
+        mbar_init(bar_accfull, 1);
+        mbar_init(bar_actready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== weight producer: one tap (hi+lo) per stage =====
+        if (lane == 0) {
+            uint32_t wc = 0;
+            for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+                for (int l = 0; l < L; l++) {
+                    for (int tap = 0; tap < 9; tap++, wc++) {
+                        const uint32_t st = wc % W_STAGES, par = (wc / W_STAGES) & 1;
+                        mbar_wait(bar_wempty + 8 * st, par ^ 1);
+                        const uint32_t bytes = l == 0 ? 2 * 2 * 64 * 16 : W_STAGE_BYTES;
+                        const void* src = l == 0 ? (const void*)(P.w_stem + (size_t)tap * (bytes / 2))
+                                                 : (const void*)(P.w_conv + ((size_t)(l - 1) * 9 + tap) * (W_STAGE_BYTES / 2));
+                        mbar_arrive_expect_tx(bar_wfull + 8 * st, bytes);
+                        bulk_g2s(smem_u32(smem + NG::OFF_W + st * W_STAGE_BYTES), src, bytes, bar_wfull + 8 * st);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t wc = 0, lc = 0;
+            const uint32_t hi_base = smem_u32(smem + NG::OFF_HI), lo_base = smem_u32(smem + NG::OFF_LO);
+            for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+                for (int l = 0; l < L; l++, lc++) {
+                    mbar_wait(bar_actready, lc & 1);
+                    tc_fence_after();
+                    // stem and every conv2 accumulate in region S (conv2 on top of the parked skip), conv1 in region A
+                    const bool is_conv1 = (l >= 1) && ((l - 1) % 2 == 0);
+                    const bool preloaded = (l >= 1) && !is_conv1;
+                    const uint32_t dcol = is_conv1 ? NG::COL_A : NG::COL_S;
+                    for (int tap = 0; tap < 9; tap++, wc++) {
+                        const uint32_t st = wc % W_STAGES, par = (wc / W_STAGES) & 1;
+                        mbar_wait(bar_wfull + 8 * st, par);
+                        tc_fence_after();
+                        const int shift = (tap / 3 - 1) * NG::PITCH + (tap % 3 - 1);
+                        const uint32_t wb = smem_u32(smem + NG::OFF_W + st * W_STAGE_BYTES);
+                        for (int t = 0; t < NG::TILES; t++) {
+                            const uint32_t row_off = (uint32_t)((NG::L0 + t * 128 + shift) * 16);
+                            const uint32_t d = tmem_base + dcol + t * 64;
+                            if (l == 0) {
+                                // K = 16: 6 input planes + zero padding, exact in fp16 -> only the weight is split
+                                const uint64_t a = umma_desc(hi_base + row_off, NG::PLANE_BYTES, 128);
+                                tc_mma_f16(d, a, umma_desc(wb, 1024, 128), IDESC_F16_M128_N64, tap > 0);
+                                tc_mma_f16(d, a, umma_desc(wb + 2048, 1024, 128), IDESC_F16_M128_N64, 1);
+                            } else {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ks++) {
+                                    const uint32_t koff = ks * 2 * NG::PLANE_BYTES;
+                                    const uint64_t ah = umma_desc(hi_base + koff + row_off, NG::PLANE_BYTES, 128);
+                                    const uint64_t al = umma_desc(lo_base + koff + row_off, NG::PLANE_BYTES, 128);
+                                    const uint64_t bh = umma_desc(wb + ks * 2048, 1024, 128);
+                                    const uint64_t bl = umma_desc(wb + 8192 + ks * 2048, 1024, 128);
+                                    tc_mma_f16(d, ah, bh, IDESC_F16_M128_N64, (preloaded || tap > 0 || ks > 0) ? 1u : 0u);
+                                    tc_mma_f16(d, al, bh, IDESC_F16_M128_N64, 1);
+                                    tc_mma_f16(d, ah, bl, IDESC_F16_M128_N64, 1);
+                                }
+                            }
+                        }
+                        tc_commit(bar_wempty + 8 * st);          // stage is free once these MMAs have read it
+                    }
+                    tc_commit(bar_accfull);                      // layer finished: accumulators complete
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps (8 warps, 256 threads) =====
+        const int et = threadIdx.x - 64;                         // 0..255
+        const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                        // which tiles: t % 2 == half
+        const float* bias_s = reinterpret_cast<const float*>(smem + NG::OFF_BIAS);
+        const float* headw_s = reinterpret_cast<const float*>(smem + NG::OFF_HEADW);
+        float* pact = reinterpret_cast<float*>(smem + NG::OFF_PACT);
+        float* vact = reinterpret_cast<float*>(smem + NG::OFF_VACT);
+        float* logit_s = reinterpret_cast<float*>(smem + NG::OFF_LOGIT);
+        uint32_t lc = 0;
+        for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+            const int slot0 = grp * G;
+            // ---- input planes -> fp16 rows (channels 0..5; 6..15 zero) ----
+            for (int r = et; r < NG::TILES * 128; r += EPI_THREADS) {
+                const int b = r / NG::BR, q = r - b * NG::BR;
+                const int y = q / NG::PITCH - 1, x = q - (y + 1) * NG::PITCH;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (b < G && y >= 0 && x < N && slot0 + b < n_slots) {
+                    const float* pl = planes + (size_t)(slot0 + b) * 6 * NG::NN + y * N + x;
+                    __half2 h01 = __floats2half2_rn(pl[0], pl[NG::NN]);
+                    __half2 h23 = __floats2half2_rn(pl[2 * NG::NN], pl[3 * NG::NN]);
+                    __half2 h45 = __floats2half2_rn(pl[4 * NG::NN], pl[5 * NG::NN]);
+                    v.x = *reinterpret_cast<uint32_t*>(&h01); v.y = *reinterpret_cast<uint32_t*>(&h23);
+                    v.z = *reinterpret_cast<uint32_t*>(&h45);
+                }
+                *reinterpret_cast<uint4*>(smem + NG::OFF_HI + (NG::L0 + r) * 16) = v;
+                *reinterpret_cast<uint4*>(smem + NG::OFF_HI + NG::PLANE_BYTES + (NG::L0 + r) * 16) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) mbar_arrive(bar_actready);
+
+            for (int l = 0; l < L; l++, lc++) {
+                const bool is_conv1 = (l >= 1) && ((l - 1) % 2 == 0);
+                const bool last = (l == L - 1);
+                const uint32_t col = is_conv1 ? NG::COL_A : NG::COL_S;
+                const float inv_scale = 1.0f / P.scale[l];
+                // scale of the next conv2 (for the parked skip): the output of the stem / a conv2 feeds block (l+1)/2's conv2 = layer l+2
+                const float next_scale = (!is_conv1 && !last) ? P.scale[l + 2] : 0.0f;
+                float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
+                mbar_wait(bar_accfull, lc & 1);
+                tc_fence_after();
+                for (int t = half; t < NG::TILES; t += 2) {
+                    const int r = t * 128 + quarter * 32 + lane;
+                    const int b = r / NG::BR, q = r - b * NG::BR;
+                    const int y = q / NG::PITCH - 1, x = q - (y + 1) * NG::PITCH;
+                    const bool interior = (b < G) && (y >= 0) && (x < N);
+                    hp0 = 0.f; hp1 = 0.f; hv = 0.f;
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + col + t * 64 + c0;
+                        TG_TMEM_LD32(taddr, v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float o[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            float f = fmaf(__uint_as_float(v[j]), inv_scale, bias_s[l * 64 + c0 + j]);
+                            f = fminf(fmaxf(f, 0.0f), 60000.0f);                       // ReLU (+ fp16 range guard)
+                            o[j] = interior ? f : 0.0f;
+                        }
+                        if (last) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                hp0 = fmaf(o[j], headw_s[c0 + j], hp0);
+                                hp1 = fmaf(o[j], headw_s[64 + c0 + j], hp1);
+                                hv = fmaf(o[j], headw_s[128 + c0 + j], hv);
+                            }
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) {
+                                uint32_t ph[4], pl[4];
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const float f0 = o[kk * 8 + 2 * e], f1 = o[kk * 8 + 2 * e + 1];
+                                    const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+                                    const __half2 hh = __halves2half2(h0, h1);
+                                    const __half2 ll = __floats2half2_rn(f0 - __half2float(h0), f1 - __half2float(h1));
+                                    ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                                    pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                                }
+                                const int off = (c0 / 8 + kk) * NG::PLANE_BYTES + (NG::L0 + r) * 16;
+                                *reinterpret_cast<uint4*>(smem + NG::OFF_HI + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                                *reinterpret_cast<uint4*>(smem + NG::OFF_LO + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                            }
+                            if (next_scale != 0.0f) {                                   // park the skip for the next block
+#pragma unroll
+                                for (int j = 0; j < 32; j++) v[j] = __float_as_uint(o[j] * next_scale);
+                                const uint32_t saddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + NG::COL_S + t * 64 + c0;
+                                TG_TMEM_ST32(saddr, v);
+                            }
+                        }
+                    }
+                    if (last && interior) {                                             // policy_head.py:34-36, value_head.py:35-37
+                        const int idx = y * N + x;
+                        pact[b * 2 * NG::NN + idx] = fmaxf(hp0 + headw_s[192], 0.0f);
+                        pact[b * 2 * NG::NN + NG::NN + idx] = fmaxf(hp1 + headw_s[193], 0.0f);
+                        vact[b * NG::NN + idx] = fmaxf(hv + headw_s[194], 0.0f);
+                    }
+                }
+                if (!last) {
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    fence_proxy_async();
+                    tc_fence_before();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (et == 0) mbar_arrive(bar_actready);
+                }
+            }
+            // ---- heads: FC layers + softmax (policy_head.py:37-40, value_head.py:38-40, dual_net.py:81-106) ----
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int o = et; o < NG::A; o += EPI_THREADS) {
+                float acc[G];
+#pragma unroll
+                for (int b = 0; b < G; b++) acc[b] = P.pfc_b[o];
+                for (int j = 0; j < 2 * NG::NN; j++) {
+                    const float w = __ldg(P.pfc_t + (size_t)j * NG::A + o);
+#pragma unroll
+                    for (int b = 0; b < G; b++) acc[b] = fmaf(w, pact[b * 2 * NG::NN + j], acc[b]);
+                }
+#pragma unroll
+                for (int b = 0; b < G; b++) logit_s[b * NG::A + o] = acc[b];
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            {
+                const int ew = warp - 2;
+                for (int b = ew; b < G; b += 8) {
+                    const int slot = slot0 + b;
+                    if (slot >= n_slots) continue;
+                    // value head: 3 logits + softmax
+                    float z[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        float s = 0.f;
+                        for (int j = lane; j < NG::NN; j += 32) s = fmaf(P.vfc_w[k * NG::NN + j], vact[b * NG::NN + j], s);
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                        z[k] = s + P.vfc_b[k];
+                    }
+                    const float zm = fmaxf(z[0], fmaxf(z[1], z[2]));
+                    const float e0 = expf(z[0] - zm), e1 = expf(z[1] - zm), e2 = expf(z[2] - zm);
+                    const float es = e0 + e1 + e2;
+                    if (lane == 0) { value[(size_t)slot * 3] = e0 / es; value[(size_t)slot * 3 + 1] = e1 / es; value[(size_t)slot * 3 + 2] = e2 / es; }
+                    // policy
+                    if (use_logit) {
+                        for (int o = lane; o < NG::A; o += 32) policy[(size_t)slot * NG::A + o] = logit_s[b * NG::A + o];
+                    } else {
+                        float mx = -3.0e38f;
+                        for (int o = lane; o < NG::A; o += 32) mx = fmaxf(mx, logit_s[b * NG::A + o]);
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        float sum = 0.f;
+                        for (int o = lane; o < NG::A; o += 32) sum += expf(logit_s[b * NG::A + o] - mx);
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                        for (int o = lane; o < NG::A; o += 32) policy[(size_t)slot * NG::A + o] = expf(logit_s[b * NG::A + o] - mx) / sum;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 CUDA-core reference path
+// ------------------------------------------------------------------------------------------------
+// out[slot][oc][p] = act( sum_{ic,tap} w[ic][tap][oc] * in[slot][ic][p+tap] + bias[oc] (+ skip) ), one block per slot.
+template <int N>
+__global__ void __launch_bounds__(256) k_conv3x3_simt(const float* __restrict__ in, int cin, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, const float* __restrict__ skip,
+                                                      float* __restrict__ out, int n_slots)
+{
+    constexpr int NN = N * N, W = N + 2, CELLS = W * W;
+    extern __shared__ float s_in[];                    // [cin][CELLS] with a zero halo
+    const int slot = blockIdx.x;
+    if (slot >= n_slots) return;
+    for (int i = threadIdx.x; i < cin * CELLS; i += 256) s_in[i] = 0.0f;
+    __syncthreads();
+    const float* src = in + (size_t)slot * cin * NN;
+    for (int i = threadIdx.x; i < cin * NN; i += 256) {
+        const int c = i / NN, p = i - c * NN;
+        s_in[c * CELLS + (p / N + 1) * W + (p % N + 1)] = src[i];
+    }
+    __syncthreads();
+    const int oc = threadIdx.x & 63, pg = threadIdx.x >> 6;
+    constexpr int PT = 8;
+    for (int p0 = pg * PT; p0 < NN; p0 += 4 * PT) {
+        float acc[PT];
+        int base[PT];
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            const int p = min(p0 + i, NN - 1);
+            acc[i] = 0.0f; base[i] = (p / N) * W + (p % N);          // top-left of the 3x3 window in the padded board
+        }
+        for (int ic = 0; ic < cin; ic++) {
+            const float* si = s_in + ic * CELLS;
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+                const float wv = __ldg(w + ((size_t)ic * 9 + tap) * 64 + oc);
+                const int off = (tap / 3) * W + (tap % 3);
+#pragma unroll
+                for (int i = 0; i < PT; i++) acc[i] = fmaf(wv, si[base[i] + off], acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            const int p = p0 + i;
+            if (p < NN) {
+                const size_t o = ((size_t)slot * 64 + oc) * NN + p;
+                float v = acc[i] + bias[oc];
+                if (skip) v += skip[o];
+                out[o] = fmaxf(v, 0.0f);
+            }
+        }
+    }
+}
+
+// heads on the CUDA cores: act [slot][64][NN] -> policy [slot][A], value [slot][3]; one block per slot
+template <int N>
+__global__ void __launch_bounds__(256) k_heads_simt(NetDev P, const float* __restrict__ act, int n_slots, int use_logit,
+                                                    float* __restrict__ policy, float* __restrict__ value)
+{
+    constexpr int NN = N * N, A = NN + 1;
+    __shared__ float pact[2 * NN];
+    __shared__ float vact[NN];
+    __shared__ float logit[A];
+    __shared__ float red[8];
+    const int slot = blockIdx.x;
+    if (slot >= n_slots) return;
+    const float* a = act + (size_t)slot * 64 * NN;
+    for (int p = threadIdx.x; p < NN; p += 256) {
+        float h0 = 0.f, h1 = 0.f, hv = 0.f;
+        for (int c = 0; c < 64; c++) {
+            const float v = a[c * NN + p];
+            h0 = fmaf(v, P.head_w[c], h0); h1 = fmaf(v, P.head_w[64 + c], h1); hv = fmaf(v, P.head_w[128 + c], hv);
+        }
+        pact[p] = fmaxf(h0 + P.head_b[0], 0.f); pact[NN + p] = fmaxf(h1 + P.head_b[1], 0.f); vact[p] = fmaxf(hv + P.head_b[2], 0.f);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < A; o += 256) {
+        float s = P.pfc_b[o];
+        for (int j = 0; j < 2 * NN; j++) s = fmaf(P.pfc_t[(size_t)j * A + o], pact[j], s);
+        logit[o] = s;
+    }
+    if (threadIdx.x < 3) {
+        float s = P.vfc_b[threadIdx.x];
+        for (int j = 0; j < NN; j++) s = fmaf(P.vfc_w[threadIdx.x * NN + j], vact[j], s);
+        red[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float zm = fmaxf(red[0], fmaxf(red[1], red[2]));
+        const float e0 = expf(red[0] - zm), e1 = expf(red[1] - zm), e2 = expf(red[2] - zm), es = e0 + e1 + e2;
+        value[(size_t)slot * 3] = e0 / es; value[(size_t)slot * 3 + 1] = e1 / es; value[(size_t)slot * 3 + 2] = e2 / es;
+        float mx = -3.0e38f;
+        for (int o = 0; o < A; o++) mx = fmaxf(mx, logit[o]);
+        float sum = 0.f;
+        for (int o = 0; o < A; o++) sum += expf(logit[o] - mx);
+        red[4] = mx; red[5] = sum;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < A; o += 256)
+        policy[(size_t)slot * A + o] = use_logit ? logit[o] : expf(logit[o] - red[4]) / red[5];
+}
+
+}  // namespace tg

@@ -1,0 +1,714 @@
+// tg_engine.cu -- host side of the engine and the C ABI (include/tamago_b200.h).
+//
+// Owns the structure-of-arrays pools in HBM (root boards, node pool, leaf queues, evaluator batch), folds and
+// packs the DualNet parameters, and queues the kernel sequence of one move of every game on one CUDA stream.
+#include "../../include/tamago_b200.h"
+#include "tg_search.cuh"
+#include "tg_dualnet.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace tg;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(TG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct tg_engine {
+    tg_config cfg{};
+    int N = 0, NN = 0, A = 0, AP = 0, CELLS = 0, CP = 0, MAXREC = 0, SNAP = 0, PLANES = 0;
+    int cap_sh = 0, cap_puct = 0, depth_sh = 64, depth_puct = 0, cap_max = 0;
+    size_t path_words = 0;
+    int slot_cap = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> events;
+    Dev D{};
+    NetDev net{};
+    std::vector<void*> allocs;
+    std::vector<void*> net_allocs;
+    // fp32 path scratch
+    float* act[3] = {nullptr, nullptr, nullptr};
+    int simt_chunk = 0;
+    // host staging (pinned)
+    int* h_gs = nullptr; int16_t* h_action = nullptr; double* h_improved = nullptr; int* h_visits = nullptr;
+    bool have_weights = false, have_zobrist = false;
+    int64_t launches = 0;
+    float last_ms = 0.f, last_eval_ms = 0.f;
+    int64_t last_eval_slots = 0;
+    int sms = 148;
+};
+
+template <class T> static int dalloc(tg_engine* e, T** p, size_t n, bool zero = true)
+{
+    void* q = nullptr;
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CK(cudaMalloc(&q, bytes));
+    if (zero) CK(cudaMemsetAsync(q, 0, bytes, e->stream));
+    e->allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// eye table (board/pattern.py:53-98): 3x3 neighbourhood codes whose centre is an eye of a colour.
+// Built geometrically: the 8 neighbours carry (dy, dx); symmetries permute coordinates.
+// ---------------------------------------------------------------------------------------------
+static const int kDy[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, kDx[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+static int cell_of(int dy, int dx) { for (int i = 0; i < 8; i++) if (kDy[i] == dy && kDx[i] == dx) return i; return -1; }
+template <class F> static unsigned pat_map(unsigned p, F f)
+{   // new neighbour (dy,dx) takes the value of the old neighbour f(dy,dx)
+    unsigned r = 0;
+    for (int i = 0; i < 8; i++) { int sy, sx; f(kDy[i], kDx[i], sy, sx); r |= ((p >> (2 * cell_of(sy, sx))) & 3u) << (2 * i); }
+    return r;
+}
+static unsigned pat_swap(unsigned p)
+{   // exchange black and white stones (pattern.py:227-236)
+    unsigned r = 0;
+    for (int i = 0; i < 8; i++) { unsigned v = (p >> (2 * i)) & 3u; v = ((v >> 1) & 1u) | ((v & 1u) << 1); r |= v << (2 * i); }
+    return r;
+}
+static void build_eye_table(std::vector<uint8_t>& eye)
+{
+    static const unsigned seeds[20] = {
+        0x5554, 0x5556, 0x5544, 0x5546, 0x1554, 0x1556, 0x1544, 0x1546, 0x1564, 0x1146,
+        0xFD54, 0xFD55, 0xFF74, 0xFF75, 0x5566, 0xFD66, 0x5965, 0x9955, 0xFD56, 0xFF76 };
+    eye.assign(65536, EMPTY);
+    auto put = [&](unsigned p) { eye[p & 0xffff] = BLACK; eye[pat_swap(p) & 0xffff] = WHITE; };
+    put(0x5555); put(0x1144);
+    auto flip_ud = [](int dy, int dx, int& sy, int& sx) { sy = -dy; sx = dx; };      // pat3_vertical_mirror
+    auto flip_lr = [](int dy, int dx, int& sy, int& sx) { sy = dy; sx = -dx; };      // pat3_horizontal_mirror
+    auto rot = [](int dy, int dx, int& sy, int& sx) { sy = dx; sx = -dy; };          // pat3_rotate_90
+    for (unsigned s : seeds) {
+        unsigned sym[8];
+        sym[0] = s; sym[1] = pat_map(s, flip_ud); sym[2] = pat_map(s, flip_lr); sym[3] = pat_map(sym[2], flip_ud);
+        for (int i = 0; i < 4; i++) sym[4 + i] = pat_map(sym[i], rot);
+        for (unsigned p : sym) put(p);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+static size_t search_smem(int N)
+{
+    switch (N) { case 9: return sizeof(WarpSmem<9>) * SEARCH_WARPS; case 13: return sizeof(WarpSmem<13>) * SEARCH_WARPS;
+                 default: return sizeof(WarpSmem<19>) * SEARCH_WARPS; }
+}
+
+#define DISPATCH_N(e, ...) do { switch ((e)->N) { \
+    case 9:  { constexpr int BN = 9;  __VA_ARGS__; } break; \
+    case 13: { constexpr int BN = 13; __VA_ARGS__; } break; \
+    case 19: { constexpr int BN = 19; __VA_ARGS__; } break; } } while (0)
+
+template <int BN> static int setup_kernel_attrs()
+{
+    const int bytes = (int)(sizeof(WarpSmem<BN>) * SEARCH_WARPS);
+    CK(cudaFuncSetAttribute(k_root_begin<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_descend_sh<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_move_end<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_reset<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_play<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_snapshot_roots<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_conv3x3_simt<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * (BN + 2) * (BN + 2) * 4));
+    return 0;
+}
+template <int BN, int G> static int setup_tc_attr()
+{
+    CK(cudaFuncSetAttribute(k_dualnet_tc<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, NetGeo<BN, G>::SMEM_BYTES));
+    return 0;
+}
+template <int BN> struct TcGroup { static constexpr int G = 1; };
+template <> struct TcGroup<9> { static constexpr int G = 5; };
+template <> struct TcGroup<13> { static constexpr int G = 2; };
+
+static int search_grid(const tg_engine* e) { return (e->cfg.games + SEARCH_WARPS - 1) / SEARCH_WARPS; }
+
+// mcts/sequential_halving.py:36-60 on the host: the longest schedule over m = min(#children, 16) sizes the phase loop
+static int sh_phases_host(int m, int visits, int* max_leaves)
+{
+    std::vector<int> cons, cnts;
+    if (m <= 1) { cons.push_back(1); cnts.push_back(visits); }
+    else {
+        const int log2max = (int)std::ceil(std::log2((double)m));
+        int total = 0, nc = m;
+        while (total < visits) {
+            int extra = std::max(1, visits / (log2max * nc));
+            for (int x = 0; x < extra && total < visits; x++) {
+                const int c = std::min(nc, visits - total);
+                total += c;
+                size_t f = 0;
+                for (; f < cons.size(); f++) if (cons[f] == c) break;
+                if (f < cons.size()) cnts[f]++; else { cons.push_back(c); cnts.push_back(1); }
+            }
+            nc = std::max(2, nc / 2);
+        }
+    }
+    int ml = 0;
+    for (size_t i = 0; i < cons.size(); i++) ml = std::max(ml, cons[i] * cnts[i]);
+    if (max_leaves) *max_leaves = ml;
+    return (int)cons.size();
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" const char* tg_last_error(void) { return g_err.c_str(); }
+extern "C" int tg_action_stride(int n) { return (n * n + 1 + 31) & ~31; }
+
+extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
+{
+    if (!cfg || !out) return fail(TG_ERR_ARG, "null argument");
+    if (cfg->board_size != 9 && cfg->board_size != 13 && cfg->board_size != 19)
+        return fail(TG_ERR_ARG, "board_size must be 9, 13 or 19");
+    if (cfg->games < 1 || cfg->max_visits < 1) return fail(TG_ERR_ARG, "games and max_visits must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(TG_ERR_CUDA, "no CUDA device: tamago_b200 has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(TG_ERR_ARG, "bad device ordinal");
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(TG_ERR_CUDA, "tamago_b200 kernels are built for sm_100a only");
+
+    tg_engine* e = new tg_engine();
+    e->cfg = *cfg;
+    if (e->cfg.batch_size < 1) e->cfg.batch_size = 1;
+    if (e->cfg.net_blocks <= 0) e->cfg.net_blocks = 6;
+    if (e->cfg.net_blocks > 15) { delete e; return fail(TG_ERR_ARG, "net_blocks must be <= 15"); }
+    const int N = cfg->board_size;
+    e->N = N; e->NN = N * N; e->A = e->NN + 1; e->AP = tg_action_stride(N);
+    e->CELLS = (N + 2) * (N + 2); e->CP = (e->CELLS + 3) & ~3; e->MAXREC = 3 * e->NN; e->PLANES = 6 * e->NN;
+    e->SNAP = (16 + e->NN + 15) & ~15;
+    e->sms = prop.multiProcessorCount;
+    const int games = cfg->games, V = cfg->max_visits;
+    const int max_nodes = cfg->max_nodes > 0 ? cfg->max_nodes : V + 2;
+    if (max_nodes >= (1 << (32 - PATH_NODE_SHIFT))) { delete e; return fail(TG_ERR_ARG, "max_nodes too large"); }
+
+    // leaf queue geometry: sequential halving enqueues a whole phase (<= V leaves, depth <= 64);
+    // PUCT enqueues batch_size leaves whose paths may be as long as the move history allows
+    int sh_leaves = 1;
+    for (int m = 1; m <= 16; m++) { int ml; sh_phases_host(m, V, &ml); sh_leaves = std::max(sh_leaves, ml); }
+    e->cap_sh = sh_leaves; e->depth_sh = 64;
+    e->cap_puct = e->cfg.batch_size; e->depth_puct = e->MAXREC + 2;
+    e->cap_max = std::max(e->cap_sh, e->cap_puct);
+    e->path_words = std::max((size_t)e->cap_sh * e->depth_sh, (size_t)e->cap_puct * e->depth_puct);
+    const size_t want_slots = (size_t)games * e->cap_max;
+    e->slot_cap = (int)std::min<size_t>(want_slots, (size_t)1 << 22);
+
+    auto bail = [&](int rc) { tg_engine_destroy(e); return rc; };
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "stream"));
+    e->events.resize(64);
+    for (auto& ev : e->events) if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "event"));
+
+    Dev& D = e->D;
+    D.games = games; D.superko = cfg->superko; D.cgos = cfg->cgos_mode; D.dedup = cfg->dedup; D.seed = cfg->seed;
+    D.cap = e->cap_sh; D.max_depth = e->depth_sh; D.slot_cap = e->slot_cap;
+    D.tree.max_nodes = max_nodes;
+    int rc = 0;
+    const size_t gn = (size_t)games * max_nodes;
+#define DA(p, n) if ((rc = dalloc(e, &(p), (n))) != 0) return bail(rc)
+    DA(D.b_color, (size_t)games * e->CP); DA(D.b_chain, (size_t)games * e->CP); DA(D.b_bloom, (size_t)games * BLOOM_WORDS);
+    DA(D.b_hash, games); DA(D.b_scal, (size_t)games * 8);
+    DA(D.hist_hash, (size_t)games * e->MAXREC); DA(D.hist_pos, (size_t)games * e->MAXREC);
+    DA(D.tree.hdr, gn * H_STRIDE); DA(D.tree.action, gn * e->AP); DA(D.tree.cidx, gn * e->AP); DA(D.tree.cval, gn * e->AP);
+    DA(D.tree.cvis, gn * e->AP); DA(D.tree.cpol, gn * e->AP); DA(D.tree.cvl, gn * e->AP); DA(D.tree.cvsum, gn * e->AP);
+    DA(D.tree.noise, (size_t)games * e->AP);
+    DA(D.gs, (size_t)games * GS_STRIDE); DA(D.game_id, games);
+    DA(D.path, (size_t)games * e->path_words); DA(D.path_len, (size_t)games * e->cap_max);
+    DA(D.leaf_node, (size_t)games * e->cap_max); DA(D.leaf_slot, (size_t)games * e->cap_max);
+    DA(D.snap, (size_t)games * e->cap_max * e->SNAP);
+    DA(D.planes, (size_t)e->slot_cap * e->PLANES); DA(D.policy, (size_t)e->slot_cap * e->A); DA(D.value, (size_t)e->slot_cap * 3);
+    DA(D.n_slots, 1);
+    DA(D.out_action, (size_t)games * e->AP); DA(D.out_improved, (size_t)games * e->AP); DA(D.out_visits, (size_t)games * e->AP);
+    {
+        u64* z; uint8_t* eye;
+        DA(z, (size_t)4 * e->CELLS); DA(eye, 65536);
+        std::vector<uint8_t> tab; build_eye_table(tab);
+        if (cudaMemcpyAsync(eye, tab.data(), 65536, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "eye table upload"));
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "sync"));
+        D.zob = z; D.eye = eye;
+    }
+    if (cfg->evaluator == TG_EVAL_DUALNET_FP32) {
+        e->simt_chunk = std::min(e->slot_cap, 8192);
+        for (int i = 0; i < 3; i++) DA(e->act[i], (size_t)e->simt_chunk * 64 * e->NN);
+    }
+#undef DA
+    if (cudaMallocHost(&e->h_gs, (size_t)games * GS_STRIDE * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&e->h_action, (size_t)games * e->AP * sizeof(int16_t)) != cudaSuccess ||
+        cudaMallocHost(&e->h_improved, (size_t)games * e->AP * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost(&e->h_visits, (size_t)games * e->AP * sizeof(int)) != cudaSuccess)
+        return bail(fail(TG_ERR_CUDA, "pinned host allocation failed"));
+
+    DISPATCH_N(e, rc = setup_kernel_attrs<BN>());
+    if (rc) return bail(rc);
+    DISPATCH_N(e, (rc = setup_tc_attr<BN, TcGroup<BN>::G>()));
+    if (rc) return bail(rc);
+
+    // default Zobrist table (splitmix64 stream); tg_set_zobrist replaces it
+    {
+        std::vector<u64> z((size_t)4 * e->CELLS);
+        for (size_t i = 0; i < z.size(); i++) z[i] = mix64(mix64(0x7A6Dull) + (u64)i);
+        if (cudaMemcpyAsync(const_cast<u64*>(D.zob), z.data(), z.size() * 8, cudaMemcpyHostToDevice, e->stream) != cudaSuccess)
+            return bail(fail(TG_ERR_CUDA, "zobrist upload"));
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "sync"));
+    }
+    *out = e;
+    rc = tg_reset(e, nullptr, nullptr, nullptr);
+    if (rc) { *out = nullptr; return bail(rc); }
+    return TG_OK;
+}
+
+static void free_net(tg_engine* e) { for (void* p : e->net_allocs) cudaFree(p); e->net_allocs.clear(); e->have_weights = false; }
+
+extern "C" void tg_engine_destroy(tg_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    free_net(e);
+    for (void* p : e->allocs) cudaFree(p);
+    for (auto ev : e->events) if (ev) cudaEventDestroy(ev);
+    if (e->h_gs) cudaFreeHost(e->h_gs);
+    if (e->h_action) cudaFreeHost(e->h_action);
+    if (e->h_improved) cudaFreeHost(e->h_improved);
+    if (e->h_visits) cudaFreeHost(e->h_visits);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int tg_set_zobrist(tg_engine* e, const uint64_t* table)
+{
+    if (!e || !table) return fail(TG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(const_cast<u64*>(e->D.zob), table, (size_t)4 * e->CELLS * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->have_zobrist = true;
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DualNet parameters: fold eval-mode BatchNorm into the convolutions, split the tensor-core operands into
+// fp16 (hi, lo) pairs under a per-layer power-of-two scale, and lay them out as UMMA B tiles.
+// ---------------------------------------------------------------------------------------------
+template <class T> static int upload(tg_engine* e, const std::vector<T>& h, const T** dptr)
+{
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(h.size(), 1) * sizeof(T)));
+    e->net_allocs.push_back(q);
+    CK(cudaMemcpyAsync(q, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    *dptr = reinterpret_cast<const T*>(q);
+    return 0;
+}
+
+extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
+{
+    if (!e || !w) return fail(TG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    free_net(e);
+    const int blocks = e->cfg.net_blocks, L = 1 + 2 * blocks, NN = e->NN, A = e->A;
+    // folded fp64 weights per layer: wf[l][oc][ic][tap], bias[l][oc]
+    std::vector<std::vector<double>> wf(L);
+    std::vector<float> bias((size_t)L * 64), scale(L);
+    auto fold = [&](int l, const float* cw, int cin, const float* bn, float eps) {
+        wf[l].assign((size_t)64 * cin * 9, 0.0);
+        for (int oc = 0; oc < 64; oc++) {
+            const double g = (double)bn[oc] / std::sqrt((double)bn[3 * 64 + oc] + (double)eps);   // weight / sqrt(running_var + eps)
+            for (int i = 0; i < cin * 9; i++) wf[l][(size_t)oc * cin * 9 + i] = (double)cw[(size_t)oc * cin * 9 + i] * g;
+            bias[(size_t)l * 64 + oc] = (float)((double)bn[64 + oc] - (double)bn[2 * 64 + oc] * g);
+        }
+    };
+    fold(0, w->conv_w, 6, w->bn, w->bn_eps);
+    for (int b = 0; b < blocks; b++)
+        for (int c = 0; c < 2; c++)
+            fold(1 + 2 * b + c, w->block_conv_w + ((size_t)b * 2 + c) * 64 * 64 * 9, 64, w->block_bn + ((size_t)b * 2 + c) * 4 * 64, w->block_bn_eps);
+
+    std::vector<__half> w_stem((size_t)9 * 2 * 2 * 64 * 8), w_conv((size_t)(L - 1) * 9 * 2 * 8 * 64 * 8);
+    std::vector<float> w32_stem((size_t)6 * 9 * 64), w32_conv((size_t)(L - 1) * 64 * 9 * 64);
+    for (int l = 0; l < L; l++) {
+        const int cin = l == 0 ? 6 : 64, chunks = l == 0 ? 2 : 8;
+        double mx = 0.0;
+        for (double v : wf[l]) mx = std::max(mx, std::fabs(v));
+        int ex = 0;
+        if (mx > 0.0) { std::frexp(mx, &ex); }                        // mx = f * 2^ex, f in [0.5, 1)
+        const double s = std::ldexp(1.0, 10 - ex);                    // scaled maximum in [512, 1024)
+        scale[l] = (float)s;
+        __half* dst = l == 0 ? w_stem.data() : w_conv.data() + (size_t)(l - 1) * 9 * 2 * 8 * 64 * 8;
+        float* d32 = l == 0 ? w32_stem.data() : w32_conv.data() + (size_t)(l - 1) * 64 * 9 * 64;
+        for (int tap = 0; tap < 9; tap++)
+            for (int oc = 0; oc < 64; oc++)
+                for (int ic = 0; ic < chunks * 8; ic++) {
+                    const double v = ic < cin ? wf[l][((size_t)oc * cin + ic) * 9 + tap] : 0.0;
+                    const double vs = v * s;
+                    const __half hi = __float2half_rn((float)vs);
+                    const __half lo = __float2half_rn((float)(vs - (double)__half2float(hi)));
+                    const size_t tapbase = (size_t)tap * 2 * chunks * 64 * 8;
+                    const size_t within = ((size_t)(ic / 8) * 64 + oc) * 8 + (ic % 8);
+                    dst[tapbase + within] = hi;
+                    dst[tapbase + (size_t)chunks * 64 * 8 + within] = lo;
+                    if (ic < cin) d32[((size_t)ic * 9 + tap) * 64 + oc] = (float)v;
+                }
+    }
+    // heads
+    std::vector<float> head_w(3 * 64), head_b(3), pfc_t((size_t)2 * NN * A), pfc_b(A), vfc_w((size_t)3 * NN), vfc_b(3);
+    for (int k = 0; k < 3; k++) {
+        const float* cw = k < 2 ? w->policy_conv_w + (size_t)k * 64 : w->value_conv_w;
+        const float* bn = k < 2 ? w->policy_bn : w->value_bn;
+        const int C = k < 2 ? 2 : 1, c = k < 2 ? k : 0;
+        const double g = (double)bn[c] / std::sqrt((double)bn[3 * C + c] + (double)w->head_bn_eps);
+        for (int i = 0; i < 64; i++) head_w[(size_t)k * 64 + i] = (float)((double)cw[i] * g);
+        head_b[k] = (float)((double)bn[C + c] - (double)bn[2 * C + c] * g);
+    }
+    for (int o = 0; o < A; o++) {
+        pfc_b[o] = w->policy_fc_b[o];
+        for (int j = 0; j < 2 * NN; j++) pfc_t[(size_t)j * A + o] = w->policy_fc_w[(size_t)o * 2 * NN + j];
+    }
+    for (int i = 0; i < 3 * NN; i++) vfc_w[i] = w->value_fc_w[i];
+    for (int i = 0; i < 3; i++) vfc_b[i] = w->value_fc_b[i];
+
+    NetDev& n = e->net;
+    n.blocks = blocks;
+    int rc;
+    if ((rc = upload(e, w_stem, &n.w_stem)) || (rc = upload(e, w_conv, &n.w_conv)) || (rc = upload(e, bias, &n.bias)) ||
+        (rc = upload(e, scale, &n.scale)) || (rc = upload(e, head_w, &n.head_w)) || (rc = upload(e, head_b, &n.head_b)) ||
+        (rc = upload(e, pfc_t, &n.pfc_t)) || (rc = upload(e, pfc_b, &n.pfc_b)) || (rc = upload(e, vfc_w, &n.vfc_w)) ||
+        (rc = upload(e, vfc_b, &n.vfc_b)) || (rc = upload(e, w32_stem, &n.w32_stem)) || (rc = upload(e, w32_conv, &n.w32_conv)))
+        return rc;
+    CK(cudaStreamSynchronize(e->stream));
+    e->have_weights = true;
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int tg_reset(tg_engine* e, const uint8_t* mask, const uint64_t* game_ids, const uint8_t* never_resign)
+{
+    if (!e) return fail(TG_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    const int games = e->cfg.games;
+    uint8_t *d_mask = nullptr, *d_nr = nullptr; u64* d_ids = nullptr;
+    std::vector<u64> ids(games);
+    for (int g = 0; g < games; g++) ids[g] = game_ids ? game_ids[g] : (u64)g;
+    CK(cudaMalloc(&d_ids, (size_t)games * 8));
+    CK(cudaMemcpyAsync(d_ids, ids.data(), (size_t)games * 8, cudaMemcpyHostToDevice, e->stream));
+    if (mask) { CK(cudaMalloc(&d_mask, games)); CK(cudaMemcpyAsync(d_mask, mask, games, cudaMemcpyHostToDevice, e->stream)); }
+    if (never_resign) { CK(cudaMalloc(&d_nr, games)); CK(cudaMemcpyAsync(d_nr, never_resign, games, cudaMemcpyHostToDevice, e->stream)); }
+    DISPATCH_N(e, (k_reset<BN><<<search_grid(e), SEARCH_WARPS * 32, search_smem(BN), e->stream>>>(e->D, d_mask, d_ids, d_nr)));
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    cudaFree(d_ids); if (d_mask) cudaFree(d_mask); if (d_nr) cudaFree(d_nr);
+    return TG_OK;
+}
+
+extern "C" int tg_set_to_move(tg_engine* e, const int32_t* colors)
+{
+    if (!e || !colors) return fail(TG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpy2DAsync(e->D.gs + GS_COLOR, GS_STRIDE * sizeof(int), colors, sizeof(int), sizeof(int), e->cfg.games,
+                         cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return TG_OK;
+}
+
+extern "C" int tg_play(tg_engine* e, const int16_t* moves, const uint8_t* colors, const int32_t* counts, int32_t stride, tg_ply_dump* dump)
+{
+    if (!e || !moves || !counts || stride < 1) return fail(TG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    const int games = e->cfg.games;
+    const size_t nm = (size_t)games * stride;
+    int16_t* d_moves = nullptr; uint8_t* d_colors = nullptr; int* d_counts = nullptr;
+    CK(cudaMalloc(&d_moves, nm * 2)); CK(cudaMalloc(&d_counts, (size_t)games * 4));
+    CK(cudaMemcpyAsync(d_moves, moves, nm * 2, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(d_counts, counts, (size_t)games * 4, cudaMemcpyHostToDevice, e->stream));
+    if (colors) { CK(cudaMalloc(&d_colors, nm)); CK(cudaMemcpyAsync(d_colors, colors, nm, cudaMemcpyHostToDevice, e->stream)); }
+    PlyDump pd{}; std::vector<void*> tmp;
+    const int plies = dump ? dump->plies : 0;
+    const size_t np = (size_t)games * std::max(plies, 1);
+    if (dump) {
+        if (plies < 1) return fail(TG_ERR_ARG, "dump->plies must be positive");
+        auto da = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return 1; tmp.push_back(*p); return 0; };
+        int bad = 0;
+        bad |= da((void**)&pd.color, np * e->CELLS); bad |= da((void**)&pd.libs, np * e->CELLS * 2); bad |= da((void**)&pd.size, np * e->CELLS * 2);
+        bad |= da((void**)&pd.scal, np * 5 * 4); bad |= da((void**)&pd.hash, np * 8);
+        bad |= da((void**)&pd.legal, np * 2 * e->NN); bad |= da((void**)&pd.satari, np * 2 * e->NN * 2);
+        bad |= da((void**)&pd.eye, np * 2 * e->NN); bad |= da((void**)&pd.cand, np * 2 * e->NN); bad |= da((void**)&pd.score, np * 4);
+        if (bad) { for (void* p : tmp) cudaFree(p); return fail(TG_ERR_CUDA, "dump allocation failed"); }
+        pd.stride = plies;
+    }
+    DISPATCH_N(e, (k_play<BN><<<search_grid(e), SEARCH_WARPS * 32, search_smem(BN), e->stream>>>(e->D, d_moves, d_colors, d_counts, stride, pd, dump ? 1 : 0)));
+    e->launches++;
+    CK(cudaGetLastError());
+    if (dump) {
+#define CP_OUT(field, bytes) if (dump->field) CK(cudaMemcpyAsync(dump->field, pd.field, (bytes), cudaMemcpyDeviceToHost, e->stream))
+        CP_OUT(color, np * e->CELLS); CP_OUT(libs, np * e->CELLS * 2); CP_OUT(size, np * e->CELLS * 2); CP_OUT(scal, np * 5 * 4);
+        CP_OUT(hash, np * 8); CP_OUT(legal, np * 2 * e->NN); CP_OUT(satari, np * 2 * e->NN * 2); CP_OUT(eye, np * 2 * e->NN);
+        CP_OUT(cand, np * 2 * e->NN); CP_OUT(score, np * 4);
+#undef CP_OUT
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    for (void* p : tmp) cudaFree(p);
+    cudaFree(d_moves); cudaFree(d_counts); if (d_colors) cudaFree(d_colors);
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// evaluator: slot bases, feature planes, network (device-side slot count; no host round trip)
+// ---------------------------------------------------------------------------------------------
+template <int BN> static int launch_net(tg_engine* e, int use_logit, int max_slots)
+{
+    const Dev& D = e->D;
+    if (e->cfg.evaluator == TG_EVAL_HASHNET) {
+        k_hashnet<BN><<<(max_slots + 3) / 4, 128, 0, e->stream>>>(D.planes, D.n_slots, use_logit, D.policy, D.value);
+        e->launches++;
+    } else if (e->cfg.evaluator == TG_EVAL_DUALNET_TC) {
+        if (!e->have_weights) return fail(TG_ERR_STATE, "tg_load_weights has not been called");
+        constexpr int G = TcGroup<BN>::G;
+        const int groups = (max_slots + G - 1) / G;
+        const int grid = std::max(1, std::min(e->sms, groups));
+        k_dualnet_tc<BN, G><<<grid, TC_THREADS, NetGeo<BN, G>::SMEM_BYTES, e->stream>>>(e->net, D.planes, D.n_slots, use_logit, D.policy, D.value);
+        e->launches++;
+    } else {
+        if (!e->have_weights) return fail(TG_ERR_STATE, "tg_load_weights has not been called");
+        // the CUDA-core path needs the slot count on the host (reference path only)
+        int n = 0;
+        CK(cudaMemcpyAsync(&n, D.n_slots, 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        const int L = 1 + 2 * e->net.blocks;
+        const int smem = 64 * (BN + 2) * (BN + 2) * 4;
+        for (int s0 = 0; s0 < n; s0 += e->simt_chunk) {
+            const int ns = std::min(e->simt_chunk, n - s0);
+            const float* in = D.planes + (size_t)s0 * 6 * BN * BN;
+            k_conv3x3_simt<BN><<<ns, 256, smem, e->stream>>>(in, 6, e->net.w32_stem, e->net.bias, nullptr, e->act[0], ns);
+            int cur = 0;
+            for (int l = 1; l < L; l += 2) {
+                const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
+                k_conv3x3_simt<BN><<<ns, 256, smem, e->stream>>>(e->act[cur], 64, e->net.w32_conv + (size_t)(l - 1) * 64 * 9 * 64,
+                                                                 e->net.bias + (size_t)l * 64, nullptr, e->act[t1], ns);
+                k_conv3x3_simt<BN><<<ns, 256, smem, e->stream>>>(e->act[t1], 64, e->net.w32_conv + (size_t)l * 64 * 9 * 64,
+                                                                 e->net.bias + (size_t)(l + 1) * 64, e->act[cur], e->act[t2], ns);
+                cur = t2;
+                e->launches += 2;
+            }
+            k_heads_simt<BN><<<ns, 256, 0, e->stream>>>(e->net, e->act[cur], ns, use_logit, D.policy + (size_t)s0 * (BN * BN + 1), D.value + (size_t)s0 * 3);
+            e->launches += 2;
+        }
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int BN> static int launch_eval(tg_engine* e, int use_logit, int max_slots, int* ev_idx)
+{
+    const Dev& D = e->D;
+    k_scan<<<1, 1024, 0, e->stream>>>(D);
+    k_planes<BN><<<D.games, 256, 16 * Snap<BN>::BYTES, e->stream>>>(D);
+    e->launches += 2;
+    const bool timed = ev_idx && *ev_idx + 2 <= (int)e->events.size();
+    if (timed) CK(cudaEventRecord(e->events[(*ev_idx)++], e->stream));
+    const int rc = launch_net<BN>(e, use_logit, std::min(max_slots, e->slot_cap));
+    if (rc) return rc;
+    if (timed) CK(cudaEventRecord(e->events[(*ev_idx)++], e->stream));
+    return 0;
+}
+
+extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t strict, int32_t play, tg_step_result* out)
+{
+    if (!e) return fail(TG_ERR_ARG, "null engine");
+    if (visits < 1 || visits > e->cfg.max_visits) return fail(TG_ERR_ARG, "visits outside [1, max_visits]");
+    if (mode != TG_MODE_SH && mode != TG_MODE_PUCT) return fail(TG_ERR_ARG, "bad mode");
+    CK(cudaSetDevice(e->cfg.device));
+    const int games = e->cfg.games, grid = search_grid(e), thr = SEARCH_WARPS * 32;
+    const int use_logit = mode == TG_MODE_SH ? 1 : 0;
+    int rc = 0, ev = 2;
+    Dev& D = e->D;
+    if (mode == TG_MODE_SH) { D.cap = e->cap_sh; D.max_depth = e->depth_sh; } else { D.cap = e->cap_puct; D.max_depth = e->depth_puct; }
+    const int max_moves = 2 * e->NN;
+    CK(cudaEventRecord(e->events[0], e->stream));
+    DISPATCH_N(e, {
+        const size_t sm = search_smem(BN);
+        k_root_begin<BN><<<grid, thr, sm, e->stream>>>(D);
+        e->launches++;
+        rc = launch_eval<BN>(e, use_logit, games, &ev);
+        if (!rc) {
+            k_backup<BN><<<grid, thr, 0, e->stream>>>(D, use_logit);
+            k_root_post<BN><<<grid, thr, 0, e->stream>>>(D, mode, visits);
+            e->launches += 2;
+            if (mode == TG_MODE_SH) {
+                int phases = 1;
+                for (int m = 1; m <= 16; m++) phases = std::max(phases, sh_phases_host(m, visits, nullptr));
+                for (int p = 0; p < phases && !rc; p++) {
+                    k_descend_sh<BN><<<grid, thr, sm, e->stream>>>(D);
+                    e->launches++;
+                    rc = launch_eval<BN>(e, 1, (int)std::min<size_t>((size_t)games * e->cap_sh, (size_t)e->slot_cap), &ev);
+                    k_backup<BN><<<grid, thr, 0, e->stream>>>(D, 1);
+                    e->launches++;
+                }
+            } else {
+                const int batch = e->cfg.batch_size;
+                const int iters = (visits + batch - 1) / batch + 1;
+                for (int it = 0; it < iters && !rc; it++) {
+                    k_descend_puct<BN><<<grid, thr, sm, e->stream>>>(D, visits, batch, strict);
+                    e->launches++;
+                    rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
+                    k_backup<BN><<<grid, thr, 0, e->stream>>>(D, 0);
+                    e->launches++;
+                }
+            }
+            if (!rc) {
+                k_move_end<BN><<<grid, thr, sm, e->stream>>>(D, mode, play, e->cfg.komi, max_moves);
+                e->launches++;
+            }
+        }
+    });
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->events[1], e->stream));
+    // results -> pinned staging -> caller
+    CK(cudaMemcpyAsync(e->h_gs, D.gs, (size_t)games * GS_STRIDE * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (out && out->action) CK(cudaMemcpyAsync(e->h_action, D.out_action, (size_t)games * e->AP * 2, cudaMemcpyDeviceToHost, e->stream));
+    if (out && out->improved) CK(cudaMemcpyAsync(e->h_improved, D.out_improved, (size_t)games * e->AP * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (out && out->visits) CK(cudaMemcpyAsync(e->h_visits, D.out_visits, (size_t)games * e->AP * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
+    e->last_eval_ms = 0.f;
+    for (int i = 2; i + 1 < ev; i += 2) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->events[i], e->events[i + 1])); e->last_eval_ms += ms; }
+    int64_t evals = 0; int any_err = 0;
+    for (int g = 0; g < games; g++) {
+        const int* gs = e->h_gs + (size_t)g * GS_STRIDE;
+        evals += gs[GS_EVALS];
+        any_err |= gs[GS_ERROR];
+        if (!out) continue;
+        if (out->move) out->move[g] = gs[GS_LAST_MOVE];
+        if (out->color) out->color[g] = gs[GS_LAST_COLOR];
+        if (out->num_children) out->num_children[g] = gs[GS_ROOT_K];
+        if (out->finished) out->finished[g] = gs[GS_FINISHED];
+        if (out->winner) out->winner[g] = gs[GS_WINNER];
+        if (out->resigned) out->resigned[g] = gs[GS_RESIGNED];
+        if (out->score) { float f; memcpy(&f, &gs[GS_SCORE], 4); out->score[g] = f; }
+        if (out->error) out->error[g] = gs[GS_ERROR];
+    }
+    e->last_eval_slots = evals;
+    if (out) {
+        if (out->action) memcpy(out->action, e->h_action, (size_t)games * e->AP * 2);
+        if (out->improved) memcpy(out->improved, e->h_improved, (size_t)games * e->AP * 8);
+        if (out->visits) memcpy(out->visits, e->h_visits, (size_t)games * e->AP * 4);
+        if (out->evals) *out->evals = evals;
+    }
+    if (any_err && !(out && out->error)) return fail(TG_ERR_SEARCH, "search error flags set (history/depth/node/queue overflow); pass tg_step_result.error to inspect");
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int tg_planes(tg_engine* e, float* outp)
+{
+    if (!e || !outp) return fail(TG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    Dev& D = e->D;
+    D.cap = e->cap_max; D.max_depth = 1;
+    if (e->slot_cap < e->cfg.games) return fail(TG_ERR_STATE, "evaluator batch smaller than the game pool");
+    DISPATCH_N(e, {
+        k_snapshot_roots<BN><<<search_grid(e), SEARCH_WARPS * 32, search_smem(BN), e->stream>>>(D);
+        k_scan<<<1, 1024, 0, e->stream>>>(D);
+        k_planes<BN><<<D.games, 256, 16 * Snap<BN>::BYTES, e->stream>>>(D);
+    });
+    e->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(outp, D.planes, (size_t)e->cfg.games * e->PLANES * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return TG_OK;
+}
+
+extern "C" int tg_forward(tg_engine* e, const float* planes, int32_t n, int32_t use_logit, float* policy, float* value)
+{
+    if (!e || !planes || !policy || !value || n < 0) return fail(TG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    const Dev& D = e->D;
+    CK(cudaEventRecord(e->events[0], e->stream));
+    for (int s0 = 0; s0 < n; s0 += e->slot_cap) {
+        const int ns = std::min(e->slot_cap, n - s0);
+        CK(cudaMemcpyAsync(D.planes, planes + (size_t)s0 * e->PLANES, (size_t)ns * e->PLANES * 4, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(D.n_slots, &ns, 4, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));                       // &ns is a stack variable
+        int rc = 0;
+        DISPATCH_N(e, rc = launch_net<BN>(e, use_logit, ns));
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(policy + (size_t)s0 * e->A, D.policy, (size_t)ns * e->A * 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(value + (size_t)s0 * 3, D.value, (size_t)ns * 3 * 4, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaEventRecord(e->events[1], e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
+    return TG_OK;
+}
+
+extern "C" int tg_tree_size(tg_engine* e, int32_t game, int32_t* num_nodes)
+{
+    if (!e || !num_nodes || game < 0 || game >= e->cfg.games) return fail(TG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaMemcpyAsync(num_nodes, e->D.gs + (size_t)game * GS_STRIDE + GS_NNODES, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return TG_OK;
+}
+
+extern "C" int tg_read_node(tg_engine* e, int32_t game, int32_t index, tg_node_view* o)
+{
+    if (!e || !o || game < 0 || game >= e->cfg.games || index < 0 || index >= e->D.tree.max_nodes) return fail(TG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    const TreePool& t = e->D.tree;
+    const size_t nb = (size_t)game * t.max_nodes + index, row = nb * e->AP;
+    int hdr[H_STRIDE];
+    CK(cudaMemcpyAsync(hdr, t.hdr + nb * H_STRIDE, sizeof hdr, cudaMemcpyDeviceToHost, e->stream));
+#define RD(dst, src, T) if (o->dst) CK(cudaMemcpyAsync(o->dst, src + row, (size_t)e->AP * sizeof(T), cudaMemcpyDeviceToHost, e->stream))
+    RD(action, t.action, int16_t); RD(children_index, t.cidx, int); RD(children_value, t.cval, float); RD(children_visits, t.cvis, int);
+    RD(children_policy, t.cpol, double); RD(children_virtual_loss, t.cvl, int); RD(children_value_sum, t.cvsum, float);
+#undef RD
+    if (o->noise) CK(cudaMemcpyAsync(o->noise, t.noise + (size_t)game * e->AP, (size_t)e->AP * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    o->num_children = hdr[H_K]; o->node_visits = hdr[H_NV]; o->virtual_loss = hdr[H_VL];
+    memcpy(&o->node_value_sum, &hdr[H_VSUM], 4); memcpy(&o->raw_value, &hdr[H_RAW], 4);
+    return TG_OK;
+}
+
+extern "C" int64_t tg_launch_count(tg_engine* e) { return e ? e->launches : 0; }
+extern "C" float tg_last_device_ms(tg_engine* e) { return e ? e->last_ms : 0.f; }
+
+// Time one kernel class on the evaluator batch as it stands (bench.py roofline legs).
+extern "C" int tg_bench_kernel(tg_engine* e, const char* name, int32_t slots, int32_t iters, float* ms_out)
+{
+    if (!e || !name || !ms_out || iters < 1) return fail(TG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    const std::string k(name);
+    slots = std::min(slots, e->slot_cap);
+    if (k == "eval_ms") { *ms_out = e->last_eval_ms; return TG_OK; }
+    if (k == "eval_slots") { *ms_out = (float)e->last_eval_slots; return TG_OK; }
+    if (k == "dualnet") {
+        CK(cudaMemcpyAsync(e->D.n_slots, &slots, 4, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        int rc = 0;
+        DISPATCH_N(e, rc = launch_net<BN>(e, 1, slots));            // warm-up
+        if (rc) return rc;
+        CK(cudaEventRecord(e->events[0], e->stream));
+        for (int i = 0; i < iters && !rc; i++) DISPATCH_N(e, rc = launch_net<BN>(e, 1, slots));
+        if (rc) return rc;
+        CK(cudaEventRecord(e->events[1], e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaEventElapsedTime(ms_out, e->events[0], e->events[1]));
+        *ms_out /= (float)iters;
+        return TG_OK;
+    }
+    if (k == "planes") {
+        // every game re-expands its current leaf snapshots (whatever the last search phase left in the queue)
+        CK(cudaEventRecord(e->events[0], e->stream));
+        for (int i = 0; i < iters; i++) DISPATCH_N(e, (k_planes<BN><<<e->D.games, 256, 16 * Snap<BN>::BYTES, e->stream>>>(e->D)));
+        e->launches += iters;
+        CK(cudaEventRecord(e->events[1], e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaEventElapsedTime(ms_out, e->events[0], e->events[1]));
+        *ms_out /= (float)iters;
+        return TG_OK;
+    }
+    return fail(TG_ERR_ARG, "unknown kernel name");
+}

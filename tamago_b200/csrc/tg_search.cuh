@@ -1,0 +1,687 @@
+// tg_search.cuh -- device side of the search: one warp walks one game's tree.
+//
+// Reference path: mcts/tree.py (expand_node 247-270, process_mini_batch 273-315,
+// generate_move_with_sequential_halving 318-356, search_by_sequential_halving 359-384,
+// search_sequential_halving 387-422, search_best_move 57-105, search 130-174,
+// search_mcts 199-244), mcts/node.py, selfplay/worker.py:46-90.
+//
+// Kernel sequence for one move of every game in the pool (host side: tg_engine.cu):
+//   k_root_begin   expand the root, enqueue it as leaf 0
+//   [k_scan, k_planes, <evaluator>, k_backup]           root evaluation
+//   k_root_post    Gumbel noise + sequential-halving schedule (SH) / single-child shortcut (PUCT)
+//   repeat: k_descend_sh | k_descend_puct, k_scan, k_planes, <evaluator>, k_backup
+//   k_move_end     final choice, resign test, improved policy, play the move, scoring
+#pragma once
+#include "tg_board.cuh"
+#include "tg_tree.cuh"
+
+namespace tg {
+
+enum : int {
+    GS_COLOR = 0, GS_NNODES = 1, GS_PHASE = 2, GS_NPHASES = 3, GS_CONS = 4, GS_CNTS = 12,
+    GS_NLEAF = 20, GS_NUNIQ = 21, GS_SLOT0 = 22, GS_ERROR = 23, GS_DONE = 24, GS_DESC = 25,
+    GS_PASSCNT = 26, GS_NMOVES = 27, GS_FINISHED = 28, GS_NEVER_RESIGN = 29, GS_LAST_MOVE = 30,
+    GS_ROOT_K = 31, GS_ACTIVE = 32, GS_WINNER = 33, GS_RESIGNED = 34, GS_SCORE = 35, GS_ROOTPASS = 36,
+    GS_LAST_COLOR = 37, GS_EVALS = 38, GS_STRIDE = 48
+};
+enum : int { ERR_DEPTH = 1, ERR_HISTORY = 2, ERR_NODES = 4, ERR_QUEUE = 8 };
+enum : int { MODE_SH = 0, MODE_PUCT = 1 };
+
+constexpr int SEARCH_WARPS = 4;           // warps (= games) per block in the search kernels
+constexpr int PATH_NODE_SHIFT = 12;       // path entry: node << 12 | child
+
+// Everything the search kernels need, passed by value.
+struct Dev {
+    int games, cap, max_depth, superko, cgos, dedup;
+    u64 seed;
+    // root boards
+    uint8_t* b_color; uint16_t* b_chain; unsigned* b_bloom; u64* b_hash; int* b_scal; u64* hist_hash; int16_t* hist_pos;
+    TreePool tree;
+    int* gs;                 // [games][GS_STRIDE]
+    u64* game_id;            // [games]
+    // leaf queue
+    unsigned* path;          // [games][cap][max_depth]
+    int* path_len;           // [games][cap]
+    int* leaf_node;          // [games][cap]  node whose priors the evaluation fills (-1: none)
+    int* leaf_slot;          // [games][cap]  slot of the leaf relative to the game's slot base
+    uint8_t* snap;           // [games][cap][Snap::BYTES]  one per unique slot
+    // evaluator batch
+    float* planes; float* policy; float* value; int* n_slots;
+    int slot_cap;
+    // per-move outputs (read back by the host)
+    int16_t* out_action;     // [games][AP]
+    double* out_improved;    // [games][AP]
+    int* out_visits;         // [games][AP]
+    // constants
+    const u64* zob; const uint8_t* eye;
+};
+
+template <int N> struct WarpSmem {
+    WBoard<N> root;
+    WBoard<N> scratch;
+    WAnalysis<N> an;
+    double s0[Geo<N>::AP];
+    double s1[Geo<N>::AP];
+};
+
+template <int N> __device__ __forceinline__ BoardPool<N> pool_of(const Dev& D)
+{
+    BoardPool<N> p;
+    p.color = D.b_color; p.chain = D.b_chain; p.bloom = D.b_bloom; p.hash = D.b_hash; p.scal = D.b_scal;
+    p.hist_hash = D.hist_hash; p.hist_pos = D.hist_pos;
+    return p;
+}
+
+// mcts/tree.py:247-270 + node.py:41-72: allocate the next node, list candidates (PASS last), tentative priors.
+template <int N>
+__device__ inline int expand_node(const Dev& D, const Tree& t, int g, int* gs, const WBoard<N>& b, WAnalysis<N>& an, const BScal& s,
+                                  int color, const u64* hist_hash, unsigned move_key, int lane)
+{
+    using G = Geo<N>;
+    const int idx = gs[GS_NNODES];
+    if (idx >= D.tree.max_nodes) { if (lane == 0) gs[GS_ERROR] |= ERR_NODES; __syncwarp(); return -1; }
+    const size_t row = (size_t)idx * G::AP;
+    int k = 0;
+    wb_analyze<N>(b, an, s, color, D.superko != 0, D.zob, D.eye, hist_hash, lane,
+        [&](int, int, int pos, bool legal, int satari, bool eye) {
+            const bool cand = legal && satari < 7 && !eye;                          // tree.py:261-263
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (cand) t.action[row + k + __popc(m & ((1u << lane) - 1))] = (int16_t)pos;
+            k += __popc(m);
+        });
+    if (lane == 0) t.action[row + k] = PASS;                                        // tree.py:264
+    k++;
+    // get_tentative_policy (tree.py:509-519): Dirichlet(1,..,1) draw from the counter-based stream
+    double part = 0.0;
+    const u64 gid = D.game_id[g];
+    for (int i = lane; i < k; i += 32) {
+        const double e = dsub(0.0, det_log(noise_u(D.seed, gid, move_key, (unsigned)idx, 0u, (unsigned)i)));
+        t.cpol[row + i] = e;
+        part = dadd(part, e);
+    }
+    const double sum = warp_shape_sum(part);
+    for (int i = lane; i < G::AP; i += 32) {
+        if (i < k) t.cpol[row + i] = ddiv(t.cpol[row + i], sum); else { t.cpol[row + i] = 0.0; t.action[row + i] = 0; }
+        t.cidx[row + i] = NOT_EXPANDED; t.cval[row + i] = 0.0f; t.cvis[row + i] = 0; t.cvl[row + i] = 0; t.cvsum[row + i] = 0.0f;
+    }
+    if (lane < H_STRIDE) t.hdr[(size_t)idx * H_STRIDE + lane] = (lane == H_K) ? k : 0;
+    if (lane == 0) gs[GS_NNODES] = idx + 1;
+    __syncwarp();
+    return idx;
+}
+
+// mcts/batch_data.py:18-27: append a leaf to the game's queue.  With dedup, a leaf reached by the same path as
+// an earlier leaf of this batch shares that leaf's evaluator slot (the position is identical).
+template <int N>
+__device__ inline void push_leaf(const Dev& D, int g, int* gs, const WBoard<N>& b, const BScal& s, int color,
+                                 const unsigned* cur_path, int plen, int node_index, int lane)
+{
+    const int i = gs[GS_NLEAF];
+    if (i >= D.cap) { if (lane == 0) gs[GS_ERROR] |= ERR_QUEUE; __syncwarp(); return; }
+    const size_t q = (size_t)g * D.cap;
+    int slot = -1;
+    if (D.dedup) {
+        for (int j = 0; j < i && slot < 0; j++) {
+            if (D.path_len[q + j] != plen) continue;
+            const unsigned* pj = D.path + (q + j) * D.max_depth;
+            bool diff = false;
+            for (int d = lane; d < plen; d += 32) diff |= (pj[d] != cur_path[d]);
+            if (!__any_sync(0xffffffffu, diff)) slot = D.leaf_slot[q + j];
+        }
+    }
+    int nu = gs[GS_NUNIQ];
+    if (slot < 0) {
+        slot = nu;
+        wb_snapshot<N>(b, s, color, D.hist_pos + (size_t)g * Geo<N>::MAXREC, D.snap + (q + slot) * Snap<N>::BYTES, lane);
+        nu++;
+    }
+    if (lane == 0) {
+        D.path_len[q + i] = plen; D.leaf_node[q + i] = node_index; D.leaf_slot[q + i] = slot;
+        gs[GS_NLEAF] = i + 1; gs[GS_NUNIQ] = nu;
+    }
+    __syncwarp();
+}
+
+template <int N>
+__device__ __forceinline__ WarpSmem<N>& warp_smem()
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    return reinterpret_cast<WarpSmem<N>*>(smem_raw)[threadIdx.x >> 5];
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_root_begin(Dev D)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (g >= D.games) return;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    if (lane == 0) { gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+    __syncwarp();
+    if (!gs[GS_ACTIVE] || gs[GS_FINISHED]) return;
+    WarpSmem<N>& sm = warp_smem<N>();
+    BScal s;
+    wb_load<N>(sm.root, s, pool_of<N>(D), g, lane);
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    if (lane == 0) {
+        gs[GS_NNODES] = 0; gs[GS_PHASE] = 0; gs[GS_NPHASES] = 0; gs[GS_DONE] = 0; gs[GS_DESC] = 0; gs[GS_ROOTPASS] = 0;
+        gs[GS_ERROR] = 0; gs[GS_EVALS] = 0;
+    }
+    __syncwarp();
+    const int color = gs[GS_COLOR];
+    const u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
+    const int root = expand_node<N>(D, t, g, gs, sm.root, sm.an, s, color, hh, (unsigned)s.moves, lane);   // tree.py:332 / 52
+    if (root < 0) return;
+    for (int i = lane; i < G::AP; i += 32) t.noise[i] = 0.0;                      // node.py:57
+    push_leaf<N>(D, g, gs, sm.root, s, color, nullptr, 0, root, lane);            // tree.py:333-334 / 53-54
+}
+
+// After the root evaluation: Gumbel noise and the halving schedule (tree.py:336, 370-373), or the
+// single-candidate shortcut of search_best_move (tree.py:76-77).
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_root_post(Dev D, int mode, int visits)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (g >= D.games) return;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    if (!gs[GS_ACTIVE] || gs[GS_FINISHED] || gs[GS_ERROR]) return;
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    const int k = t.hdr[H_K];
+    if (lane == 0) gs[GS_ROOT_K] = k;
+    if (mode == MODE_SH) {
+        const u64 gid = D.game_id[g];
+        const unsigned mv = (unsigned)D.b_scal[(size_t)g * 8 + 0];
+        for (int i = lane; i < G::A; i += 32) {                                   // node.py:275-278: gumbel(size=MAX_ACTIONS)
+            const double e = dsub(0.0, det_log(noise_u(D.seed, gid, mv, 0u, 1u, (unsigned)i)));
+            t.noise[i] = dsub(0.0, det_log(e));
+        }
+        if (lane == 0) {
+            int cons[8], cnts[8];
+            const int np = sh_schedule(min(k, MAX_CONSIDERED), visits, cons, cnts, 8);
+            for (int i = 0; i < 8; i++) { gs[GS_CONS + i] = i < np ? cons[i] : 0; gs[GS_CNTS + i] = i < np ? cnts[i] : 0; }
+            gs[GS_NPHASES] = np; gs[GS_PHASE] = 0;
+        }
+    } else if (lane == 0 && k == 1) { gs[GS_DONE] = 1; gs[GS_ROOTPASS] = 1; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One phase of search_by_sequential_halving (tree.py:375-384): cnt rounds x cons descents, all enqueued.
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_sh(Dev D)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (g >= D.games) return;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    if (lane == 0) { gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+    __syncwarp();
+    if (!gs[GS_ACTIVE] || gs[GS_FINISHED] || gs[GS_ERROR]) return;
+    const int phase = gs[GS_PHASE];
+    if (phase >= gs[GS_NPHASES]) return;
+    const int cons = gs[GS_CONS + phase], cnt = gs[GS_CNTS + phase];
+    WarpSmem<N>& sm = warp_smem<N>();
+    BScal rs;
+    wb_load<N>(sm.root, rs, pool_of<N>(D), g, lane);
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    const int root_color = gs[GS_COLOR];
+    u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
+    int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
+    const unsigned move_key = (unsigned)rs.moves;
+    for (int thr = 1; thr <= cnt; thr++) {
+        for (int j = 0; j < cons; j++) {
+            wb_copy<N>(sm.scratch, sm.root, lane);                               // tree.py:378
+            BScal s = rs;
+            int color = root_color, cur = 0, plen = 0;
+            const int li = gs[GS_NLEAF];
+            if (li >= D.cap) { if (lane == 0) gs[GS_ERROR] |= ERR_QUEUE; __syncwarp(); return; }
+            unsigned* path = D.path + ((size_t)g * D.cap + li) * D.max_depth;
+            for (;;) {                                                           // tree.py:387-422
+                const int next = (cur == 0) ? select_sh_root<G::AP>(t, cur, thr, lane)
+                                            : select_sh_node<G::AP>(t, cur, sm.s0, sm.s1, lane);
+                const size_t row = (size_t)cur * G::AP;
+                const int mv = t.action[row + next];
+                if (lane == 0) path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+                plen++;
+                wb_put_stone<N>(sm.scratch, s, mv, color, D.zob, hh, hp, lane);  // :407
+                color = opp(color);
+                if (lane == 0) { t.hdr[(size_t)cur * H_STRIDE + H_VL] += 1; t.cvl[row + next] += 1; }   // node.py:76-83
+                __syncwarp();
+                if (t.cvis[row + next] < 1) {                                    // :412-416
+                    push_leaf<N>(D, g, gs, sm.scratch, s, color, path, plen, t.cidx[row + next], lane);
+                    break;
+                }
+                int ci = t.cidx[row + next];
+                if (ci == NOT_EXPANDED) {                                        // :418-420
+                    ci = expand_node<N>(D, t, g, gs, sm.scratch, sm.an, s, color, hh, move_key, lane);
+                    if (ci < 0) return;
+                    if (lane == 0) t.cidx[row + next] = ci;
+                    __syncwarp();
+                }
+                cur = ci;
+                if (plen >= D.max_depth) { if (lane == 0) gs[GS_ERROR] |= ERR_DEPTH; __syncwarp(); return; }
+            }
+        }
+    }
+    if (lane == 0) gs[GS_PHASE] = phase + 1;
+}
+
+// Up to `batch` descents of search_mcts (tree.py:199-244) with the early stop of TimeManager.is_move_decided
+// (time_manager.py:146-163) checked after every descent as in MCTSTree.search (tree.py:146-152).
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int visits, int batch, int strict)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (g >= D.games) return;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    if (lane == 0) { gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+    __syncwarp();
+    if (!gs[GS_ACTIVE] || gs[GS_FINISHED] || gs[GS_ERROR] || gs[GS_DONE]) return;
+    WarpSmem<N>& sm = warp_smem<N>();
+    BScal rs;
+    wb_load<N>(sm.root, rs, pool_of<N>(D), g, lane);
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    const int root_color = gs[GS_COLOR];
+    u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
+    int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
+    const unsigned move_key = (unsigned)rs.moves;
+    for (int b = 0; b < batch; b++) {
+        int desc = gs[GS_DESC];
+        if (desc >= visits) { if (lane == 0) gs[GS_DONE] = 1; __syncwarp(); break; }
+        if (desc > 0) {
+            // is_move_decided (time_manager.py:146-163), evaluated after the previous descent and after the
+            // mini-batch flush that descent may have triggered (tree.py:149-152, 240-241):
+            // sorted(children_visits)[-1] - [-2] against the remaining budget
+            const int k = t.hdr[H_K];
+            int top1 = 0;
+            for (int i = lane; i < k; i += 32) top1 = max(top1, t.cvis[i]);
+            top1 = warp_max_i(top1);
+            int nmax = 0, top2 = 0;
+            for (int i = lane; i < k; i += 32) { const int v = t.cvis[i]; if (v == top1) nmax++; else top2 = max(top2, v); }
+            nmax = warp_sum_i(nmax); top2 = warp_max_i(top2);
+            if (nmax >= 2) top2 = top1;
+            const int remaining = visits - t.hdr[H_NV];
+            const int cutoff = strict ? 0 : top1 - top2;
+            if (remaining < cutoff) { if (lane == 0) gs[GS_DONE] = 1; __syncwarp(); break; }
+        }
+        wb_copy<N>(sm.scratch, sm.root, lane);                                   // tree.py:147
+        BScal s = rs;
+        int color = root_color, cur = 0, plen = 0;
+        unsigned* path = D.path + ((size_t)g * D.cap + gs[GS_NLEAF]) * D.max_depth;
+        bool fail = false;
+        for (;;) {
+            const int next = select_puct<G::AP>(t, cur, D.cgos != 0, lane);      // :213
+            const size_t row = (size_t)cur * G::AP;
+            const int mv = t.action[row + next];
+            if (lane == 0) path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+            plen++;
+            wb_put_stone<N>(sm.scratch, s, mv, color, D.zob, hh, hp, lane);      // :217
+            color = opp(color);
+            if (lane == 0) { t.hdr[(size_t)cur * H_STRIDE + H_VL] += 1; t.cvl[row + next] += 1; }      // :221
+            __syncwarp();
+            int expand_threshold = 1;
+            if (s.moves > 2) {                                                   // :224-229
+                if (s.moves - 1 >= G::MAXREC) { if (lane == 0) gs[GS_ERROR] |= ERR_HISTORY; fail = true; break; }
+                if (hp[s.moves - 1] == PASS && hp[s.moves - 2] == PASS) expand_threshold = 10000000;
+            }
+            if (t.cvis[row + next] + t.cvl[row + next] < expand_threshold + 1) { // :231-241
+                int ci = t.cidx[row + next];
+                if (ci == NOT_EXPANDED) {
+                    ci = expand_node<N>(D, t, g, gs, sm.scratch, sm.an, s, color, hh, move_key, lane);
+                    if (ci < 0) { fail = true; break; }
+                    if (lane == 0) t.cidx[row + next] = ci;
+                    __syncwarp();
+                }
+                push_leaf<N>(D, g, gs, sm.scratch, s, color, path, plen, ci, lane);
+                break;
+            }
+            cur = t.cidx[row + next];
+            if (plen >= D.max_depth) { if (lane == 0) gs[GS_ERROR] |= ERR_DEPTH; fail = true; break; }
+        }
+        __syncwarp();
+        if (fail) break;
+        if (lane == 0) gs[GS_DESC] = desc + 1;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exclusive scan of the per-game unique-leaf counts -> slot bases; one block.
+__global__ void __launch_bounds__(1024) k_scan(Dev D)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < D.games; base += 1024) {
+        const int g = base + threadIdx.x;
+        const int v = g < D.games ? D.gs[(size_t)g * GS_STRIDE + GS_NUNIQ] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warp_tot[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
+            warp_tot[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int prefix = carry + (threadIdx.x >= 32 ? warp_tot[(threadIdx.x >> 5) - 1] : 0) + x - v;
+        if (g < D.games) D.gs[(size_t)g * GS_STRIDE + GS_SLOT0] = prefix;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *D.n_slots = min(carry, D.slot_cap);
+}
+
+// K3 feature planes (nn/feature.py:10-57): one block per game expands its leaf snapshots into fp32 planes
+// [slot][6][N*N], written with coalesced 4-byte stores over the game's contiguous slot range.
+template <int N>
+__global__ void __launch_bounds__(256) k_planes(Dev D)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x;
+    const int* gs = D.gs + (size_t)g * GS_STRIDE;
+    const int nu = gs[GS_NUNIQ], slot0 = gs[GS_SLOT0];
+    if (nu == 0) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CH = 16;                                   // snapshots staged per pass
+    for (int u0 = 0; u0 < nu; u0 += CH) {
+        const int nc = min(CH, nu - u0);
+        const uint4* src = reinterpret_cast<const uint4*>(D.snap + ((size_t)g * D.cap + u0) * Snap<N>::BYTES);
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+        for (int i = threadIdx.x; i < nc * (Snap<N>::BYTES / 16); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        const int total = nc * G::PLANES;
+        if (slot0 + u0 + nc <= D.slot_cap) {
+            float* out = D.planes + (size_t)(slot0 + u0) * G::PLANES;
+            for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                const int u = i / G::PLANES, r = i - u * G::PLANES, p = r / G::NN, idx = r - p * G::NN;
+                out[i] = snap_plane_value<N>(smem_raw + u * Snap<N>::BYTES, p, idx);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// process_mini_batch after the forward pass (tree.py:287-315): priors/raw value of the evaluated node, then the
+// value walks the path back to the root.  Leaves of a game are applied in queue order (fp32 sums depend on it);
+// the plies of one path touch distinct nodes and are updated by different lanes.
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_backup(Dev D, int use_logit)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (g >= D.games) return;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    const int nl = gs[GS_NLEAF];
+    if (nl == 0) return;
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    const int slot0 = gs[GS_SLOT0];
+    const size_t q = (size_t)g * D.cap;
+    for (int i = 0; i < nl; i++) {
+        const int slot = slot0 + D.leaf_slot[q + i];
+        if (slot >= D.slot_cap) { if (lane == 0) gs[GS_ERROR] |= ERR_QUEUE; break; }
+        const float* pol = D.policy + (size_t)slot * G::A;
+        const float* v = D.value + (size_t)slot * 3;
+        const float v0 = v[0], v1 = v[1], v2 = v[2];
+        const int ni = D.leaf_node[q + i];
+        if (ni >= 0) {                                                           // node.py:86-93, tree.py:287-300
+            const size_t row = (size_t)ni * G::AP;
+            const int k = t.hdr[(size_t)ni * H_STRIDE + H_K];
+            for (int c = lane; c < k; c += 32) {
+                const int a = t.action[row + c];
+                float p;
+                if (a == PASS) { p = pol[G::NN]; if (use_logit) p = __fsub_rn(p, 0.5f); }              // :292-294
+                else p = pol[(a / G::W - 1) * N + (a % G::W - 1)];
+                t.cpol[row + c] = (double)p;
+            }
+            if (lane == 0) t.hdr[(size_t)ni * H_STRIDE + H_RAW] = __float_as_int(__fadd_rn(__fmul_rn(v1, 0.5f), v2));   // :300
+        }
+        const int plen = D.path_len[q + i];
+        if (plen > 0) {
+            const unsigned* path = D.path + (q + i) * D.max_depth;
+            const float val0 = __fadd_rn(v0, __fmul_rn(v1, 0.5f));               // :303
+            const float val1 = __fsub_rn(1.0f, val0), val2 = __fsub_rn(1.0f, val1);
+            for (int d0 = 0; d0 < plen; d0 += 32) {
+                const int d = d0 + lane;                                         // distance from the leaf
+                if (d < plen) {
+                    const unsigned e = path[plen - 1 - d];
+                    const int node = (int)(e >> PATH_NODE_SHIFT), c = (int)(e & ((1u << PATH_NODE_SHIFT) - 1));
+                    const float val = d == 0 ? val0 : ((d & 1) ? val1 : val2);   // value = 1 - value per ply (:313)
+                    const size_t row = (size_t)node * G::AP;
+                    if (d == 0) t.cval[row + c] = val0;                          // :308
+                    t.cvsum[row + c] = __fadd_rn(t.cvsum[row + c], val);         // node.py:118-138
+                    t.cvis[row + c] += 1; t.cvl[row + c] -= 1;
+                    int* h = t.hdr + (size_t)node * H_STRIDE;
+                    h[H_VSUM] = __float_as_int(__fadd_rn(__int_as_float(h[H_VSUM]), val));
+                    h[H_NV] += 1; h[H_VL] -= 1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) gs[GS_EVALS] += nl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// End of a move: final choice (tree.py:344-356 / 86-105), record (selfplay_record.py:45-64) and, when `play`,
+// the game loop body of selfplay/worker.py:58-87 (play the move, pass/resign/terminal handling, scoring).
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_move_end(Dev D, int mode, int play, float komi, int max_moves)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (g >= D.games) return;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    if (!gs[GS_ACTIVE] || gs[GS_FINISHED]) { if (lane == 0) gs[GS_LAST_MOVE] = -2; return; }
+    if (gs[GS_ERROR]) { if (lane == 0) { gs[GS_LAST_MOVE] = -2; gs[GS_FINISHED] = 1; } return; }
+    WarpSmem<N>& sm = warp_smem<N>();
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    const int k = t.hdr[H_K];
+    int next, move; bool resign = false;
+    if (mode == MODE_SH) {
+        next = select_sh_root<G::AP>(t, 0, PLAYOUTS, lane);                      // tree.py:344
+        const double value = value_evaluation<G::AP>(t, 0, next);
+        resign = !gs[GS_NEVER_RESIGN] && value < 0.05;                           // :353
+        move = t.action[next];
+    } else if (gs[GS_ROOTPASS]) { next = 0; move = PASS; }                      // tree.py:76-77
+    else {
+        next = best_visit_child<G::AP>(t, 0, lane);                              // :86-87
+        resign = value_evaluation<G::AP>(t, 0, next) < 0.05;                     // :100-103
+        move = t.action[next];
+    }
+    // record what selfplay_record.save_record reads from the root
+    improved_policy<G::AP>(t, 0, sm.s0, sm.s1, lane);
+    for (int i = lane; i < G::AP; i += 32) {
+        D.out_action[(size_t)g * G::AP + i] = i < k ? t.action[i] : (int16_t)0;
+        D.out_improved[(size_t)g * G::AP + i] = i < k ? sm.s0[i] : 0.0;
+        D.out_visits[(size_t)g * G::AP + i] = i < k ? t.cvis[i] : 0;
+    }
+    const int color = gs[GS_COLOR];
+    if (lane == 0) { gs[GS_LAST_MOVE] = resign ? RESIGN : move; gs[GS_LAST_COLOR] = color; }
+    if (!play) return;
+    if (resign) {                                                                // worker.py:60-63
+        if (lane == 0) { gs[GS_WINNER] = opp(color); gs[GS_RESIGNED] = 1; gs[GS_FINISHED] = 1; gs[GS_SCORE] = __float_as_int(0.0f); }
+        return;
+    }
+    BScal s;
+    wb_load<N>(sm.root, s, pool_of<N>(D), g, lane);
+    wb_put_stone<N>(sm.root, s, move, color, D.zob, D.hist_hash + (size_t)g * G::MAXREC, D.hist_pos + (size_t)g * G::MAXREC, lane);
+    wb_store<N>(sm.root, s, pool_of<N>(D), g, lane);
+    const int pass_count = move == PASS ? gs[GS_PASSCNT] + 1 : 0;                // worker.py:67-70
+    const int nmoves = gs[GS_NMOVES] + 1;
+    __syncwarp();
+    if (lane == 0) { gs[GS_PASSCNT] = pass_count; gs[GS_NMOVES] = nmoves; gs[GS_COLOR] = opp(color); }
+    if (pass_count == 2) {                                                       // :76-87
+        uint8_t* tmp = reinterpret_cast<uint8_t*>(sm.scratch.color);
+        const int sc = wb_count_score<N>(sm.root, tmp, lane);
+        const float score = (float)sc - komi;
+        if (lane == 0) {
+            gs[GS_SCORE] = __float_as_int(score);
+            gs[GS_WINNER] = score > 0.1f ? BLACK : (score < -0.1f ? WHITE : OB);
+            gs[GS_RESIGNED] = 0; gs[GS_FINISHED] = 1;
+        }
+    } else if (nmoves >= max_moves && lane == 0) {                               // :56 loop bound: winner stays EMPTY
+        gs[GS_WINNER] = EMPTY; gs[GS_RESIGNED] = 0; gs[GS_FINISHED] = 1; gs[GS_SCORE] = __float_as_int(0.0f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Board-only kernels behind the C ABI (parity tests and the position setup of genmove).
+
+// Reset the games flagged in `mask` (nullptr: all) to an empty board and a fresh game id.
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_reset(Dev D, const uint8_t* mask, const u64* new_ids, const uint8_t* never_resign)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (g >= D.games) return;
+    if (mask && !mask[g]) return;
+    WarpSmem<N>& sm = warp_smem<N>();
+    BScal s;
+    wb_clear<N>(sm.root, s, lane);
+    wb_store<N>(sm.root, s, pool_of<N>(D), g, lane);
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    for (int i = lane; i < GS_STRIDE; i += 32) gs[i] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        gs[GS_COLOR] = BLACK; gs[GS_ACTIVE] = 1;
+        gs[GS_NEVER_RESIGN] = never_resign ? never_resign[g] : 0;
+        if (new_ids) D.game_id[g] = new_ids[g];
+        D.hist_hash[(size_t)g * G::MAXREC] = 0; D.hist_pos[(size_t)g * G::MAXREC] = 0;
+    }
+}
+
+// Play moves[g][0..count[g]) on each root board, colours alternating from the stored colour to move unless
+// `colors` is given.  Optionally dumps the per-ply state for the parity tests.
+struct PlyDump {
+    uint8_t* color;      // [games][plies][CELLS]
+    int16_t* libs;       // [games][plies][CELLS]   liberties of the string on the point (0 when empty)
+    int16_t* size;       // [games][plies][CELLS]
+    int* scal;           // [games][plies][5]       moves, ko_pos, ko_move, prisoner[0], prisoner[1]
+    u64* hash;           // [games][plies]
+    uint8_t* legal;      // [games][plies][2][NN]
+    int16_t* satari;     // [games][plies][2][NN]
+    uint8_t* eye;        // [games][plies][2][NN]
+    uint8_t* cand;       // [games][plies][2][NN]
+    int* score;          // [games][plies]
+    int stride;          // plies allocated per game
+};
+
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_play(Dev D, const int16_t* moves, const uint8_t* colors, const int* count,
+                                                            int stride, PlyDump dump, int do_dump)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (g >= D.games) return;
+    const int n = count[g];
+    if (n == 0) return;
+    WarpSmem<N>& sm = warp_smem<N>();
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    BScal s;
+    wb_load<N>(sm.root, s, pool_of<N>(D), g, lane);
+    u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
+    int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
+    int color = gs[GS_COLOR];
+    for (int i = 0; i < n; i++) {
+        const int mv = moves[(size_t)g * stride + i];
+        if (colors) color = colors[(size_t)g * stride + i];
+        wb_put_stone<N>(sm.root, s, mv, color, D.zob, hh, hp, lane);
+        color = opp(color);
+        if (do_dump) {
+            const size_t pi = (size_t)g * dump.stride + i;
+            for (int c = lane; c < G::CELLS; c += 32) {
+                const int col = sm.root.color[c];
+                const bool stone = (col == BLACK || col == WHITE);
+                const unsigned ls = stone ? sm.root.ls[sm.root.chain[c]] : 0u;
+                dump.color[pi * G::CELLS + c] = (uint8_t)col;
+                dump.libs[pi * G::CELLS + c] = (int16_t)(ls >> 16);
+                dump.size[pi * G::CELLS + c] = (int16_t)(ls & 0xffffu);
+            }
+            if (lane == 0) {
+                int* sc = dump.scal + pi * 5;
+                sc[0] = s.moves; sc[1] = s.ko_pos; sc[2] = s.ko_move; sc[3] = s.pris0; sc[4] = s.pris1;
+                dump.hash[pi] = s.hash;
+            }
+            for (int ci = 0; ci < 2; ci++) {
+                const int col = ci == 0 ? BLACK : WHITE;
+                const size_t ob = (pi * 2 + ci) * G::NN;
+                wb_analyze<N>(sm.root, sm.an, s, col, D.superko != 0, D.zob, D.eye, hh, lane,
+                    [&](int, int idx, int, bool legal, int satari, bool eye) {
+                        if (idx < G::NN) {
+                            dump.legal[ob + idx] = legal ? 1 : 0;
+                            dump.satari[ob + idx] = legal ? (int16_t)satari : (int16_t)0;
+                            dump.eye[ob + idx] = (legal && eye) ? 1 : 0;
+                            dump.cand[ob + idx] = (legal && satari < 7 && !eye) ? 1 : 0;
+                        }
+                    });
+            }
+            uint8_t* tmp = reinterpret_cast<uint8_t*>(sm.scratch.color);
+            const int score = wb_count_score<N>(sm.root, tmp, lane);
+            if (lane == 0) dump.score[pi] = score;
+        }
+    }
+    wb_store<N>(sm.root, s, pool_of<N>(D), g, lane);
+    if (lane == 0) gs[GS_COLOR] = color;
+}
+
+// Snapshot the root boards as leaf 0 of every game (used by the stand-alone feature-plane entry point).
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_snapshot_roots(Dev D)
+{
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (g >= D.games) return;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    WarpSmem<N>& sm = warp_smem<N>();
+    BScal s;
+    wb_load<N>(sm.root, s, pool_of<N>(D), g, lane);
+    if (lane == 0) { gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+    __syncwarp();
+    push_leaf<N>(D, g, gs, sm.root, s, gs[GS_COLOR], nullptr, 0, -1, lane);
+}
+
+// Test evaluator: the hash "network" of oracle.hashnet (exactly representable fp32 outputs), one warp per slot.
+template <int N>
+__global__ void __launch_bounds__(128) k_hashnet(const float* planes, const int* n_slots, int use_logit, float* policy, float* value)
+{
+    using G = Geo<N>;
+    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = lane_id();
+    if (slot >= *n_slots) return;
+    const float* pl = planes + (size_t)slot * G::PLANES;
+    u64 h = 0;
+    for (int j = lane; j < G::PLANES; j += 32) {
+        const u64 code = (u64)(long long)(pl[j] + 1.0f);
+        h += mix64(3ull * (u64)j + code);
+    }
+    {   // 64-bit wrap-around sum across the warp
+        unsigned lo = (unsigned)h, hi = (unsigned)(h >> 32);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned olo = __shfl_xor_sync(0xffffffffu, lo, o), ohi = __shfl_xor_sync(0xffffffffu, hi, o);
+            const u64 a = ((u64)hi << 32) | lo, b = ((u64)ohi << 32) | olo, c = a + b;
+            lo = (unsigned)c; hi = (unsigned)(c >> 32);
+        }
+        h = ((u64)hi << 32) | lo;
+    }
+    for (int i = lane; i < G::A; i += 32) {
+        const u64 r = mix64(h + (u64)i);
+        const float raw = (float)((r >> 40) & 0xFFFFull);
+        policy[(size_t)slot * G::A + i] = use_logit ? __fsub_rn(__fdiv_rn(raw, 8192.0f), 4.0f) : __fdiv_rn(raw, 1048576.0f);
+    }
+    if (lane == 0) {
+        const float va = (float)(mix64(h + 1000ull) & 0xFFull), vb = (float)(mix64(h + 1001ull) & 0xFFull);
+        const float v0 = __fdiv_rn(va, 512.0f), v1 = __fdiv_rn(vb, 512.0f);
+        value[(size_t)slot * 3 + 0] = v0; value[(size_t)slot * 3 + 1] = v1;
+        value[(size_t)slot * 3 + 2] = __fsub_rn(__fsub_rn(1.0f, v0), v1);
+    }
+}
+
+}  // namespace tg

@@ -1,0 +1,209 @@
+// tg_tree.cuh -- flat MCTS node pool and warp-cooperative selection rules.
+//
+// Reference: mcts/node.py (MCTSNode 18-39, select_next_action 141-157,
+// calculate_completed_q_value 281-305, calculate_improved_policy 308-321,
+// select_move_by_sequential_halving_for_root 324-346, ..._for_node 349-361),
+// mcts/pucb/pucb.py:8-29, mcts/sequential_halving.py:7-60.
+//
+// One warp owns one game's tree.  Child statistics are rows of AP entries per
+// node (structure of arrays); a selection sweeps a row 32 children at a time
+// and finishes with a warp-shuffle argmax that keeps numpy's first-index tie
+// break.  All float64 arithmetic uses single correctly rounded operations
+// (tg_detmath.cuh) so decisions are bit-identical to the reference's numpy math.
+#pragma once
+#include "tg_common.cuh"
+#include "tg_detmath.cuh"
+
+namespace tg {
+
+enum : int { H_K = 0, H_NV = 1, H_VL = 2, H_VSUM = 3, H_RAW = 4, H_STRIDE = 8 };
+
+// Pointers to one game's slice of the node pool.
+struct Tree {
+    int*      hdr;     // [max_nodes][H_STRIDE]
+    int16_t*  action;  // [max_nodes][AP]      node.py:30
+    int*      cidx;    // children_index        node.py:31
+    float*    cval;    // children_value        node.py:32
+    int*      cvis;    // children_visits       node.py:33
+    double*   cpol;    // children_policy       node.py:34
+    int*      cvl;     // children_virtual_loss node.py:35
+    float*    cvsum;   // children_value_sum    node.py:36 (fp32-accumulated: the addend is a torch scalar)
+    double*   noise;   // [AP] root noise       node.py:37
+};
+
+struct TreePool {
+    int*      hdr;  int16_t* action;  int* cidx;  float* cval;  int* cvis;  double* cpol;  int* cvl;  float* cvsum;
+    double*   noise;
+    int       max_nodes;
+};
+
+template <int AP> __device__ __forceinline__ Tree tree_of(const TreePool& p, int g)
+{
+    Tree t;
+    const size_t nb = (size_t)g * p.max_nodes;
+    t.hdr = p.hdr + nb * H_STRIDE;
+    t.action = p.action + nb * AP;  t.cidx = p.cidx + nb * AP;  t.cval = p.cval + nb * AP;  t.cvis = p.cvis + nb * AP;
+    t.cpol = p.cpol + nb * AP;      t.cvl = p.cvl + nb * AP;    t.cvsum = p.cvsum + nb * AP;
+    t.noise = p.noise + (size_t)g * AP;
+    return t;
+}
+
+// node.py:141-157 + pucb.py:8-29.  Returns the child index (warp-uniform).
+template <int AP>
+__device__ inline int select_puct(const Tree& t, int node, bool cgos, int lane)
+{
+    const int* h = t.hdr + (size_t)node * H_STRIDE;
+    const int k = h[H_K];
+    const double sq = sqrt((double)(h[H_NV] + h[H_VL] + 1));
+    const size_t row = (size_t)node * AP;
+    double bv = 0.0; int bi = 0x7fffffff;
+    for (int i = lane; i < k; i += 32) {
+        const int cv = t.cvis[row + i] + t.cvl[row + i];
+        const double q = cv != 0 ? ddiv((double)t.cvsum[row + i], (double)cv) : 0.0;
+        const double u = ddiv(dmul(dmul(1.0, t.cpol[row + i]), sq), (double)(cv + 1));
+        double v = dadd(q, u);
+        if (cgos && i == k - 1) v = dsub(v, 0.1);
+        if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
+    }
+    warp_argmax_d(bv, bi);
+    return bi;
+}
+
+// node.py:324-346
+template <int AP>
+__device__ inline int select_sh_root(const Tree& t, int node, int thr, int lane)
+{
+    const int k = t.hdr[(size_t)node * H_STRIDE + H_K];
+    const size_t row = (size_t)node * AP;
+    int mx = 0;
+    for (int i = lane; i < k; i += 32) mx = max(mx, t.cvis[row + i]);
+    mx = warp_max_i(mx);
+    const double sigma = dmul((double)(C_VISIT + mx), C_SCALE);
+    double bv = 0.0; int bi = 0x7fffffff;
+    for (int i = lane; i < k; i += 32) {
+        const int vis = t.cvis[row + i];
+        const int cnt = vis + t.cvl[row + i];
+        const double q = vis > 0 ? ddiv((double)t.cvsum[row + i], (double)vis) : 0.0;
+        const double v = cnt >= thr ? -10000.0 : dadd(dadd(t.cpol[row + i], t.noise[i]), dmul(sigma, q));
+        if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
+    }
+    warp_argmax_d(bv, bi);
+    return bi;
+}
+
+// nn/utility.py:125-136 on a shared-memory vector (in place allowed: out may alias in)
+__device__ inline void softmax_smem(const double* in, double* out, int k, int lane)
+{
+    double mx = -1.0e300;
+    for (int i = lane; i < k; i += 32) mx = fmax(mx, in[i]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, shfl_xor_d(mx, o));
+    for (int i = lane; i < k; i += 32) out[i] = det_exp(dsub(in[i], mx));
+    __syncwarp();
+    const double s = np_sum(out, k, lane);
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) out[i] = ddiv(out[i], s);
+    __syncwarp();
+}
+
+// node.py:281-321.  s0, s1: two shared-memory vectors of >= k doubles; the result is left in s0.
+template <int AP>
+__device__ inline void improved_policy(const Tree& t, int node, double* s0, double* s1, int lane)
+{
+    const int* h = t.hdr + (size_t)node * H_STRIDE;
+    const int k = h[H_K], nv = h[H_NV];
+    const float raw = __int_as_float(h[H_RAW]);
+    const size_t row = (size_t)node * AP;
+    int mx = 0;
+    for (int i = lane; i < k; i += 32) mx = max(mx, t.cvis[row + i]);
+    mx = warp_max_i(mx);
+    const double sigma = dmul((double)(C_VISIT + mx), C_SCALE);
+    for (int i = lane; i < k; i += 32) s1[i] = t.cpol[row + i];
+    __syncwarp();
+    softmax_smem(s1, s0, k, lane);                                   // s0 = softmax(prior)
+    const double sum_prob = np_sum(s0, k, lane);
+    for (int i = lane; i < k; i += 32) {
+        const int vis = t.cvis[row + i];
+        const double q = vis > 0 ? ddiv((double)t.cvsum[row + i], (double)vis) : 0.0;
+        s1[i] = dmul(s0[i], q);
+    }
+    __syncwarp();
+    const double v_pi = np_sum(s1, k, lane);
+    const double vmix = ddiv(dadd(dmul((double)raw, 1.0), ddiv(dmul((double)nv, v_pi), sum_prob)), dadd((double)nv, 1.0));
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+        const int vis = t.cvis[row + i];
+        const double cq = vis > 0 ? ddiv((double)t.cvsum[row + i], (double)vis) : vmix;
+        s1[i] = dadd(t.cpol[row + i], dmul(sigma, cq));
+    }
+    __syncwarp();
+    softmax_smem(s1, s0, k, lane);
+}
+
+// node.py:349-361
+template <int AP>
+__device__ inline int select_sh_node(const Tree& t, int node, double* s0, double* s1, int lane)
+{
+    improved_policy<AP>(t, node, s0, s1, lane);
+    const int* h = t.hdr + (size_t)node * H_STRIDE;
+    const int k = h[H_K];
+    const double den = dadd(1.0, (double)h[H_NV]);
+    const size_t row = (size_t)node * AP;
+    double bv = 0.0; int bi = 0x7fffffff;
+    for (int i = lane; i < k; i += 32) {
+        const double v = dsub(s0[i], ddiv((double)t.cvis[row + i], den));
+        if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
+    }
+    warp_argmax_d(bv, bi);
+    __syncwarp();
+    return bi;
+}
+
+// node.py:169-175 (first index of the maximum visit count)
+template <int AP>
+__device__ inline int best_visit_child(const Tree& t, int node, int lane)
+{
+    const int k = t.hdr[(size_t)node * H_STRIDE + H_K];
+    const size_t row = (size_t)node * AP;
+    double bv = 0.0; int bi = 0x7fffffff;
+    for (int i = lane; i < k; i += 32) {
+        const double v = (double)t.cvis[row + i];
+        if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
+    }
+    warp_argmax_d(bv, bi);
+    return bi;
+}
+
+// node.py:364-375
+template <int AP>
+__device__ __forceinline__ double value_evaluation(const Tree& t, int node, int child)
+{
+    const size_t row = (size_t)node * AP;
+    const int vis = t.cvis[row + child];
+    return vis == 0 ? 0.5 : ddiv((double)t.cvsum[row + child], (double)vis);
+}
+
+// mcts/sequential_halving.py:7-60: {num_considered -> rounds}, insertion ordered.  Scalar code (lane 0).
+__device__ inline int sh_schedule(int m, int visits, int* considered, int* counts, int cap)
+{
+    int np = 0;
+    if (m <= 1) { considered[0] = 1; counts[0] = visits; return visits > 0 ? 1 : 0; }
+    const int log2max = m <= 2 ? 1 : (m <= 4 ? 2 : (m <= 8 ? 3 : (m <= 16 ? 4 : 5)));
+    int total = 0, nc = m;
+    while (total < visits) {
+        int extra = visits / (log2max * nc);
+        if (extra < 1) extra = 1;
+        for (int e = 0; e < extra && total < visits; e++) {
+            const int c = min(nc, visits - total);
+            total += c;
+            int f = -1;
+            for (int j = 0; j < np; j++) if (considered[j] == c) f = j;
+            if (f >= 0) counts[f]++;
+            else if (np < cap) { considered[np] = c; counts[np] = 1; np++; }
+        }
+        nc = max(2, nc / 2);
+    }
+    return np;
+}
+
+}  // namespace tg
