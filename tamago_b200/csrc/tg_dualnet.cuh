@@ -9,11 +9,15 @@
 //     halo-padded boards.  A 3x3 tap is then nothing but a row shift of the operand's start address, so the nine
 //     taps are nine shared-memory descriptors over the same buffer (no im2col, no copies);
 //   * fp32-grade accuracy from fp16 operands: x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, three MMAs accumulating
-//     into the same fp32 TMEM tile (error ~2^-22 per product; the reference net is fp32, tolerance 1e-4);
+//     into the same fp32 TMEM tile (the reference net is fp32, tolerance 1e-4).  Two details matter for the
+//     last digit: x_lo is stored scaled by 2^11 (against a 2^-11-scaled copy of w_hi) so it never becomes an
+//     fp16 subnormal, and each layer runs the two small correction terms for all nine taps FIRST and the big
+//     x_hi*w_hi terms LAST -- the tensor core truncates when it adds into the accumulator, and the truncation
+//     error scales with the accumulator's magnitude at that moment;
 //   * BatchNorm (eval mode) is folded into the weights/bias on the host; the residual skip never touches
-//     memory: the block input is parked in a second TMEM region and conv2 accumulates on top of it;
-//   * weights (16 KB per tap: hi+lo) stream from L2 through a 4-stage cp.async.bulk/mbarrier ring;
-//   * warp roles: 0 = weight producer, 1 = MMA issuer, 2..9 = epilogue (TMEM -> bias/ReLU/split -> smem) and heads.
+//     memory: the block input is parked in a second TMEM region and added in conv2's epilogue;
+//   * weights stream from L2 through a 4-stage cp.async.bulk/mbarrier ring (pass 1: 16 KB per tap, pass 2: 8 KB);
+//   * warp roles: 0 = weight producer, 1 = MMA issuer, 2..17 = epilogue (TMEM -> bias/ReLU/split -> smem) and heads.
 //
 // k_conv3x3_simt / k_heads_simt: plain fp32 CUDA-core implementation of the same network, used as the on-device
 // numerical reference for the tensor-core kernel and for board sizes without a tensor-core instantiation.
@@ -25,13 +29,17 @@ namespace tg {
 
 constexpr int NET_F = 64;                 // filters (dual_net.py:25)
 constexpr int W_STAGES = 4;
-constexpr int W_STAGE_BYTES = 2 * 8 * 64 * 16;      // hi+lo, 8 chunks x 64 oc x 16 B = 16 KB
+constexpr int W_STAGE_BYTES = 2 * 8 * 64 * 16;      // two operand copies, 8 chunks x 64 oc x 16 B = 16 KB
+constexpr int W_COPY_BYTES = 8 * 64 * 16;           // one 64x64 fp16 weight tile (8 KB)
+constexpr int W_STEM_COPY_BYTES = 2 * 64 * 16;      // one 64x16 stem tile (2 KB)
+constexpr int W_LAYER_HALVES = 9 * 3 * (W_COPY_BYTES / 2);   // fp16 elements per 64->64 layer (3 copies per tap)
+constexpr float LO_SCALE = 2048.0f;                 // x_lo is stored as x_lo * 2^11
 
 struct NetDev {
     int blocks;                  // residual blocks (dual_net.py:26)
     // tensor-core operands
-    const __half* w_stem;        // [9 taps][2 terms][2 chunks][64 oc][8 ic]
-    const __half* w_conv;        // [2*blocks][9 taps][2 terms][8 chunks][64 oc][8 ic]
+    const __half* w_stem;        // pass 1: [9 taps][w_lo][2 chunks][64 oc][8 ic], then pass 2: [9 taps][w_hi][2][64][8]
+    const __half* w_conv;        // per layer: pass 1 [9 taps][w_hi*2^-11, w_lo][8 chunks][64 oc][8 ic], pass 2 [9 taps][w_hi][8][64][8]
     const float* bias;           // [1+2*blocks][64]   BN-folded bias
     const float* scale;          // [1+2*blocks]       power-of-two weight scale of the layer
     // heads (fp32)
@@ -84,6 +92,24 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Same instruction with the descriptors given as their low words (start address | LBO) plus the shared high
+// word (SBO | version): the issuing thread only does 32-bit adds between MMAs.
+__device__ __forceinline__ void tc_mma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 // no-swizzle K-major operand: rows 16 B apart inside an 8-row core matrix, SBO between 8-row groups,
 // LBO between the two 8-element K chunks of one K=16 step (cute::UMMA::SmemDescriptor, version 1)
@@ -144,8 +170,9 @@ template <int N, int G> struct NetGeo {
     static constexpr int SMEM_BYTES = OFF_BAR + 128;
 };
 
-constexpr int TC_THREADS = 320;           // 10 warps
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARPS = 16;             // 4 per TMEM lane quarter
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + EPI_THREADS;   // + producer warp + MMA warp
 
 template <int N, int G>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -193,17 +220,24 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== weight producer: one tap (hi+lo) per stage =====
+        // ===== weight producer: per layer 9 pass-1 stages (two copies) then 9 pass-2 stages (one copy) =====
         if (lane == 0) {
             uint32_t wc = 0;
             for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
                 for (int l = 0; l < L; l++) {
-                    for (int tap = 0; tap < 9; tap++, wc++) {
+                    for (int it = 0; it < 18; it++, wc++) {
                         const uint32_t st = wc % W_STAGES, par = (wc / W_STAGES) & 1;
                         mbar_wait(bar_wempty + 8 * st, par ^ 1);
-                        const uint32_t bytes = l == 0 ? 2 * 2 * 64 * 16 : W_STAGE_BYTES;
-                        const void* src = l == 0 ? (const void*)(P.w_stem + (size_t)tap * (bytes / 2))
-                                                 : (const void*)(P.w_conv + ((size_t)(l - 1) * 9 + tap) * (W_STAGE_BYTES / 2));
+                        const int pass = it / 9, tap = it % 9;
+                        uint32_t bytes; const __half* src;
+                        if (l == 0) {
+                            bytes = W_STEM_COPY_BYTES;
+                            src = P.w_stem + (size_t)(pass * 9 + tap) * (W_STEM_COPY_BYTES / 2);
+                        } else {
+                            const __half* lw = P.w_conv + (size_t)(l - 1) * W_LAYER_HALVES;
+                            bytes = pass == 0 ? 2 * W_COPY_BYTES : W_COPY_BYTES;
+                            src = pass == 0 ? lw + (size_t)tap * W_COPY_BYTES : lw + (size_t)9 * W_COPY_BYTES + (size_t)tap * (W_COPY_BYTES / 2);
+                        }
                         mbar_arrive_expect_tx(bar_wfull + 8 * st, bytes);
                         bulk_g2s(smem_u32(smem + NG::OFF_W + st * W_STAGE_BYTES), src, bytes, bar_wfull + 8 * st);
                     }
@@ -211,57 +245,66 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: the warp walks the pipeline together, one elected lane issues =====
+        {
             uint32_t wc = 0, lc = 0;
-            const uint32_t hi_base = smem_u32(smem + NG::OFF_HI), lo_base = smem_u32(smem + NG::OFF_LO);
+            // descriptor low words: (address >> 4) | (LBO >> 4) << 16; high word: (SBO >> 4) | version 1
+            const uint32_t a_hi0 = ((smem_u32(smem + NG::OFF_HI) >> 4) & 0x3FFFu) | ((uint32_t)(NG::PLANE_BYTES >> 4) << 16);
+            const uint32_t a_lo0 = ((smem_u32(smem + NG::OFF_LO) >> 4) & 0x3FFFu) | ((uint32_t)(NG::PLANE_BYTES >> 4) << 16);
+            const uint32_t w0 = ((smem_u32(smem + NG::OFF_W) >> 4) & 0x3FFFu) | ((1024u >> 4) << 16);
+            constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+            constexpr uint32_t KS16 = 2 * NG::PLANE_BYTES / 16;      // A advance per K=16 step, in 16-byte units
             for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
                 for (int l = 0; l < L; l++, lc++) {
                     mbar_wait(bar_actready, lc & 1);
                     tc_fence_after();
-                    // stem and every conv2 accumulate in region S (conv2 on top of the parked skip), conv1 in region A
-                    const bool is_conv1 = (l >= 1) && ((l - 1) % 2 == 0);
-                    const bool preloaded = (l >= 1) && !is_conv1;
-                    const uint32_t dcol = is_conv1 ? NG::COL_A : NG::COL_S;
-                    for (int tap = 0; tap < 9; tap++, wc++) {
+                    // pass 1: the small correction terms of all taps; pass 2: the x_hi*w_hi terms (see file header)
+                    for (int it = 0; it < 18; it++, wc++) {
                         const uint32_t st = wc % W_STAGES, par = (wc / W_STAGES) & 1;
                         mbar_wait(bar_wfull + 8 * st, par);
                         tc_fence_after();
-                        const int shift = (tap / 3 - 1) * NG::PITCH + (tap % 3 - 1);
-                        const uint32_t wb = smem_u32(smem + NG::OFF_W + st * W_STAGE_BYTES);
-                        for (int t = 0; t < NG::TILES; t++) {
-                            const uint32_t row_off = (uint32_t)((NG::L0 + t * 128 + shift) * 16);
-                            const uint32_t d = tmem_base + dcol + t * 64;
-                            if (l == 0) {
-                                // K = 16: 6 input planes + zero padding, exact in fp16 -> only the weight is split
-                                const uint64_t a = umma_desc(hi_base + row_off, NG::PLANE_BYTES, 128);
-                                tc_mma_f16(d, a, umma_desc(wb, 1024, 128), IDESC_F16_M128_N64, tap > 0);
-                                tc_mma_f16(d, a, umma_desc(wb + 2048, 1024, 128), IDESC_F16_M128_N64, 1);
-                            } else {
+                        const int tap = it >= 9 ? it - 9 : it;
+                        const uint32_t row16 = (uint32_t)(NG::L0 + (tap / 3 - 1) * NG::PITCH + (tap % 3 - 1));
+                        const uint32_t ah = a_hi0 + row16, al = a_lo0 + row16;
+                        const uint32_t wb = w0 + st * (W_STAGE_BYTES / 16);
+                        const uint32_t d0 = tmem_base + NG::COL_A;
+                        if (elect_one()) {
+                        if (l == 0) {
+                            // K = 16: 6 input planes + zero padding, exact in fp16 -> only the weight is split
+#pragma unroll
+                            for (int t = 0; t < NG::TILES; t++)
+                                tc_mma_f16_w(d0 + t * 64, ah + t * 128, wb, DESC_HI, IDESC_F16_M128_N64, it > 0);
+                        } else if (it < 9) {
+#pragma unroll
+                            for (int t = 0; t < NG::TILES; t++) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ks++) {
-                                    const uint32_t koff = ks * 2 * NG::PLANE_BYTES;
-                                    const uint64_t ah = umma_desc(hi_base + koff + row_off, NG::PLANE_BYTES, 128);
-                                    const uint64_t al = umma_desc(lo_base + koff + row_off, NG::PLANE_BYTES, 128);
-                                    const uint64_t bh = umma_desc(wb + ks * 2048, 1024, 128);
-                                    const uint64_t bl = umma_desc(wb + 8192 + ks * 2048, 1024, 128);
-                                    tc_mma_f16(d, ah, bh, IDESC_F16_M128_N64, (preloaded || tap > 0 || ks > 0) ? 1u : 0u);
-                                    tc_mma_f16(d, al, bh, IDESC_F16_M128_N64, 1);
-                                    tc_mma_f16(d, ah, bl, IDESC_F16_M128_N64, 1);
+                                    tc_mma_f16_w(d0 + t * 64, al + t * 128 + ks * KS16, wb + ks * 128, DESC_HI, IDESC_F16_M128_N64,
+                                                 (it > 0 || ks > 0) ? 1u : 0u);                          // x_lo*2^11 . w_hi*2^-11
+                                    tc_mma_f16_w(d0 + t * 64, ah + t * 128 + ks * KS16, wb + 512 + ks * 128, DESC_HI, IDESC_F16_M128_N64, 1u);   // x_hi . w_lo
                                 }
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < NG::TILES; t++) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ks++)
+                                    tc_mma_f16_w(d0 + t * 64, ah + t * 128 + ks * KS16, wb + ks * 128, DESC_HI, IDESC_F16_M128_N64, 1u);         // x_hi . w_hi
                             }
                         }
                         tc_commit(bar_wempty + 8 * st);          // stage is free once these MMAs have read it
+                        if (it == 17) tc_commit(bar_accfull);    // layer finished: accumulators complete
+                        }
+                        __syncwarp();
                     }
-                    tc_commit(bar_accfull);                      // layer finished: accumulators complete
                 }
             }
         }
     } else {
         // ===== epilogue warps (8 warps, 256 threads) =====
-        const int et = threadIdx.x - 64;                         // 0..255
+        const int et = threadIdx.x - 64;                         // 0..EPI_THREADS-1
         const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                        // which tiles: t % 2 == half
+        const int tile0 = (warp - 2) >> 2;                       // which tiles: t % 4 == tile0
         const float* bias_s = reinterpret_cast<const float*>(smem + NG::OFF_BIAS);
         const float* headw_s = reinterpret_cast<const float*>(smem + NG::OFF_HEADW);
         float* pact = reinterpret_cast<float*>(smem + NG::OFF_PACT);
@@ -288,38 +331,41 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
             }
             fence_proxy_async();
             tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             if (et == 0) mbar_arrive(bar_actready);
 
             for (int l = 0; l < L; l++, lc++) {
                 const bool is_conv1 = (l >= 1) && ((l - 1) % 2 == 0);
+                const bool is_conv2 = (l >= 2) && !is_conv1;
                 const bool last = (l == L - 1);
-                const uint32_t col = is_conv1 ? NG::COL_A : NG::COL_S;
                 const float inv_scale = 1.0f / P.scale[l];
-                // scale of the next conv2 (for the parked skip): the output of the stem / a conv2 feeds block (l+1)/2's conv2 = layer l+2
-                const float next_scale = (!is_conv1 && !last) ? P.scale[l + 2] : 0.0f;
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
                 mbar_wait(bar_accfull, lc & 1);
                 tc_fence_after();
-                for (int t = half; t < NG::TILES; t += 2) {
+                for (int t = tile0; t < NG::TILES; t += EPI_WARPS / 4) {
                     const int r = t * 128 + quarter * 32 + lane;
                     const int b = r / NG::BR, q = r - b * NG::BR;
                     const int y = q / NG::PITCH - 1, x = q - (y + 1) * NG::PITCH;
                     const bool interior = (b < G) && (y >= 0) && (x < N);
+                    const float cap = interior ? 60000.0f : 0.0f;                      // halo rows stay zero; fp16 range guard
                     hp0 = 0.f; hp1 = 0.f; hv = 0.f;
 #pragma unroll
                     for (int c0 = 0; c0 < 64; c0 += 32) {
                         uint32_t v[32];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + col + t * 64 + c0;
-                        TG_TMEM_LD32(taddr, v);
+                        const uint32_t lane_col = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 64 + c0;
+                        TG_TMEM_LD32(lane_col + NG::COL_A, v);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                         float o[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            float f = fmaf(__uint_as_float(v[j]), inv_scale, bias_s[l * 64 + c0 + j]);
-                            f = fminf(fmaxf(f, 0.0f), 60000.0f);                       // ReLU (+ fp16 range guard)
-                            o[j] = interior ? f : 0.0f;
+                        for (int j = 0; j < 32; j++) o[j] = fmaf(__uint_as_float(v[j]), inv_scale, bias_s[l * 64 + c0 + j]);
+                        if (is_conv2) {                                                 // res_block.py:39: relu(input + hidden_2)
+                            TG_TMEM_LD32(lane_col + NG::COL_S, v);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int j = 0; j < 32; j++) o[j] += __uint_as_float(v[j]);
                         }
+#pragma unroll
+                        for (int j = 0; j < 32; j++) o[j] = fminf(fmaxf(o[j], 0.0f), cap);   // ReLU
                         if (last) {
 #pragma unroll
                             for (int j = 0; j < 32; j++) {
@@ -336,7 +382,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                                     const float f0 = o[kk * 8 + 2 * e], f1 = o[kk * 8 + 2 * e + 1];
                                     const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
                                     const __half2 hh = __halves2half2(h0, h1);
-                                    const __half2 ll = __floats2half2_rn(f0 - __half2float(h0), f1 - __half2float(h1));
+                                    const __half2 ll = __floats2half2_rn((f0 - __half2float(h0)) * LO_SCALE, (f1 - __half2float(h1)) * LO_SCALE);
                                     ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
                                     pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
                                 }
@@ -344,11 +390,10 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                                 *reinterpret_cast<uint4*>(smem + NG::OFF_HI + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                                 *reinterpret_cast<uint4*>(smem + NG::OFF_LO + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                             }
-                            if (next_scale != 0.0f) {                                   // park the skip for the next block
+                            if (!is_conv1) {                                            // park the block input for the next skip
 #pragma unroll
-                                for (int j = 0; j < 32; j++) v[j] = __float_as_uint(o[j] * next_scale);
-                                const uint32_t saddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + NG::COL_S + t * 64 + c0;
-                                TG_TMEM_ST32(saddr, v);
+                                for (int j = 0; j < 32; j++) v[j] = __float_as_uint(o[j]);
+                                TG_TMEM_ST32(lane_col + NG::COL_S, v);
                             }
                         }
                     }
@@ -363,13 +408,13 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     fence_proxy_async();
                     tc_fence_before();
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 1, 512;" ::: "memory");
                     if (et == 0) mbar_arrive(bar_actready);
                 }
             }
             // ---- heads: FC layers + softmax (policy_head.py:37-40, value_head.py:38-40, dual_net.py:81-106) ----
             tc_fence_before();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             for (int o = et; o < NG::A; o += EPI_THREADS) {
                 float acc[G];
 #pragma unroll
@@ -382,10 +427,10 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
 #pragma unroll
                 for (int b = 0; b < G; b++) logit_s[b * NG::A + o] = acc[b];
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             {
                 const int ew = warp - 2;
-                for (int b = ew; b < G; b += 8) {
+                for (int b = ew; b < G; b += EPI_WARPS) {
                     const int slot = slot0 + b;
                     if (slot >= n_slots) continue;
                     // value head: 3 logits + softmax
@@ -418,7 +463,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                     }
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
         }
     }
     // ---- teardown ----

@@ -326,7 +326,8 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
         for (int c = 0; c < 2; c++)
             fold(1 + 2 * b + c, w->block_conv_w + ((size_t)b * 2 + c) * 64 * 64 * 9, 64, w->block_bn + ((size_t)b * 2 + c) * 4 * 64, w->block_bn_eps);
 
-    std::vector<__half> w_stem((size_t)9 * 2 * 2 * 64 * 8), w_conv((size_t)(L - 1) * 9 * 2 * 8 * 64 * 8);
+    const size_t stem_copy = (size_t)W_STEM_COPY_BYTES / 2, conv_copy = (size_t)W_COPY_BYTES / 2;
+    std::vector<__half> w_stem(18 * stem_copy), w_conv((size_t)(L - 1) * W_LAYER_HALVES);
     std::vector<float> w32_stem((size_t)6 * 9 * 64), w32_conv((size_t)(L - 1) * 64 * 9 * 64);
     for (int l = 0; l < L; l++) {
         const int cin = l == 0 ? 6 : 64, chunks = l == 0 ? 2 : 8;
@@ -334,9 +335,9 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
         for (double v : wf[l]) mx = std::max(mx, std::fabs(v));
         int ex = 0;
         if (mx > 0.0) { std::frexp(mx, &ex); }                        // mx = f * 2^ex, f in [0.5, 1)
-        const double s = std::ldexp(1.0, 10 - ex);                    // scaled maximum in [512, 1024)
+        const double s = std::ldexp(1.0, 14 - ex);                    // scaled maximum in [2^13, 2^14)
         scale[l] = (float)s;
-        __half* dst = l == 0 ? w_stem.data() : w_conv.data() + (size_t)(l - 1) * 9 * 2 * 8 * 64 * 8;
+        __half* lw = l == 0 ? w_stem.data() : w_conv.data() + (size_t)(l - 1) * W_LAYER_HALVES;
         float* d32 = l == 0 ? w32_stem.data() : w32_conv.data() + (size_t)(l - 1) * 64 * 9 * 64;
         for (int tap = 0; tap < 9; tap++)
             for (int oc = 0; oc < 64; oc++)
@@ -345,10 +346,16 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
                     const double vs = v * s;
                     const __half hi = __float2half_rn((float)vs);
                     const __half lo = __float2half_rn((float)(vs - (double)__half2float(hi)));
-                    const size_t tapbase = (size_t)tap * 2 * chunks * 64 * 8;
+                    const __half his = __float2half_rn(__half2float(hi) / LO_SCALE);          // pairs with x_lo * 2^11
                     const size_t within = ((size_t)(ic / 8) * 64 + oc) * 8 + (ic % 8);
-                    dst[tapbase + within] = hi;
-                    dst[tapbase + (size_t)chunks * 64 * 8 + within] = lo;
+                    if (l == 0) {
+                        lw[(size_t)tap * stem_copy + within] = lo;                             // pass 1
+                        lw[(size_t)(9 + tap) * stem_copy + within] = hi;                       // pass 2
+                    } else {
+                        lw[(size_t)tap * 2 * conv_copy + within] = his;                        // pass 1, copy 0
+                        lw[(size_t)tap * 2 * conv_copy + conv_copy + within] = lo;             // pass 1, copy 1
+                        lw[(size_t)18 * conv_copy + (size_t)tap * conv_copy + within] = hi;    // pass 2
+                    }
                     if (ic < cin) d32[((size_t)ic * 9 + tap) * 64 + oc] = (float)v;
                 }
     }

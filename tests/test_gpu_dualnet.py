@@ -37,9 +37,35 @@ def test_dualnet_matches_reference_golden(golden_dir, size, evaluator):
     e.close()
 
 
+def _torch_dualnet_f64(sd, x, size):
+    """fp64 restatement of DualNet.forward (dual_net.py:41-52, res_block.py:27-39, head/*.py) with torch ops."""
+    import torch
+    import torch.nn.functional as F
+    dev = "cuda"
+    t = {k: torch.from_numpy(np.asarray(v)).to(dev).double() for k, v in sd.items() if not k.endswith("num_batches_tracked")}
+
+    def bn(h, p, eps):
+        return F.batch_norm(h, t[p + ".running_mean"], t[p + ".running_var"], t[p + ".weight"], t[p + ".bias"], False, 0.0, eps)
+    h = torch.from_numpy(x).to(dev).double()
+    h = F.relu(bn(F.conv2d(h, t["conv_layer.weight"], padding=1), "bn_layer", 1e-5))
+    b = 0
+    while f"blocks.{b}.conv1.weight" in t:
+        h1 = F.relu(bn(F.conv2d(h, t[f"blocks.{b}.conv1.weight"], padding=1), f"blocks.{b}.bn1", 2e-5))
+        h2 = bn(F.conv2d(h1, t[f"blocks.{b}.conv2.weight"], padding=1), f"blocks.{b}.bn2", 2e-5)
+        h = F.relu(h + h2)
+        b += 1
+    p = F.relu(bn(F.conv2d(h, t["policy_head.conv_layer.weight"]), "policy_head.bn_layer", 2e-5)).flatten(1)
+    logits = p @ t["policy_head.fc_layer.weight"].T + t["policy_head.fc_layer.bias"]
+    v = F.relu(bn(F.conv2d(h, t["value_head.conv_layer.weight"]), "value_head.bn_layer", 2e-5)).flatten(1)
+    vlog = v @ t["value_head.fc_layer.weight"].T + t["value_head.fc_layer.bias"]
+    return logits.cpu().numpy(), torch.softmax(vlog, 1).cpu().numpy()
+
+
 @pytest.mark.parametrize("size", [9, 19])
-def test_tensor_core_kernel_matches_fp32_kernel_on_large_batch(golden_dir, size):
-    """Ragged batch sizes (group remainders, several waves of CTAs): tcgen05 path vs the CUDA-core fp32 path."""
+def test_kernels_match_fp64_reference_on_large_ragged_batch(golden_dir, size):
+    """Ragged batch sizes (group remainders, several waves of CTAs): both kernels against an fp64 evaluation of the
+    same network, 1e-4 on logits and values.  The policy FC of the seeded weights is scaled so that logits stay in the
+    range of trained networks (|logit| < ~10); the error of any fp32-accumulating implementation scales with it."""
     import tamago_b200 as tb
     g = np.load(os.path.join(golden_dir, f"dualnet_{size}.npz"))
     rs = np.random.RandomState(3)
@@ -52,12 +78,14 @@ def test_tensor_core_kernel_matches_fp32_kernel_on_large_batch(golden_dir, size)
     for c in range(3):
         x[:, c][flip] = (cls[flip] == c).astype(np.float32)
     sd = _weights(size, 4242)
-    out = {}
+    sd["policy_head.fc_layer.weight"] = (sd["policy_head.fc_layer.weight"] * 0.3).astype(np.float32)
+    ref_logits, ref_val = _torch_dualnet_f64(sd, x, size)
+    print(f"size {size}: |logit| max {np.abs(ref_logits).max():.2f}")
     for name, ev in (("tc", tb.EVAL_DUALNET_TC), ("fp32", tb.EVAL_DUALNET_FP32)):
         e = tb.Engine(board_size=size, games=64, max_visits=32, evaluator=ev)
         e.load_state_dict(sd)
-        out[name] = e.forward(x, use_logit=True)
+        logits, val = e.forward(x, use_logit=True)
         e.close()
-    assert np.abs(out["tc"][0] - out["fp32"][0]).max() <= TOL
-    assert np.abs(out["tc"][1] - out["fp32"][1]).max() <= TOL
-    assert np.isfinite(out["tc"][0]).all()
+        dl, dv = np.abs(logits - ref_logits).max(), np.abs(val - ref_val).max()
+        print(f"size {size} {name}: max |dlogit| {dl:.3e}, |dvalue| {dv:.3e} vs fp64")
+        assert np.isfinite(logits).all() and dl <= TOL and dv <= TOL
