@@ -95,7 +95,7 @@ typedef struct tg_step_result {
     int32_t* resigned;      /* [games]                                                                     */
     float*   score;         /* [games] count_score() - komi (worker.py:81)                                 */
     int32_t* error;         /* [games] search error bits (0 = ok)                                          */
-    int64_t* evals;         /* [1] network evaluations executed by this call                               */
+    int64_t* evals;         /* [2] leaf evaluations requested by the search, evaluations executed (differ with dedup) */
 } tg_step_result;
 
 /* One node of a game's tree (MCTSNode, mcts/node.py:18-39), for tree-parity tests and get_root(). */

@@ -17,7 +17,8 @@
 //   * BatchNorm (eval mode) is folded into the weights/bias on the host; the residual skip never touches
 //     memory: the block input is parked in a second TMEM region and added in conv2's epilogue;
 //   * weights stream from L2 through a 4-stage cp.async.bulk/mbarrier ring (pass 1: 16 KB per tap, pass 2: 8 KB);
-//   * warp roles: 0 = weight producer, 1 = MMA issuer, 2..17 = epilogue (TMEM -> bias/ReLU/split -> smem) and heads.
+//   * warp roles: 0..15 = epilogue (TMEM -> bias/ReLU/split -> smem) and heads, 16 = weight producer, 17 = MMA issuer
+//     (the highest warp id: it must never wait for an issue slot behind the epilogue warps).
 //
 // k_conv3x3_simt / k_heads_simt: plain fp32 CUDA-core implementation of the same network, used as the on-device
 // numerical reference for the tensor-core kernel and for board sizes without a tensor-core instantiation.
@@ -69,11 +70,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}"
-        :: "r"(bar), "r"(parity) : "memory");
+        :: "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 {
@@ -172,7 +173,8 @@ template <int N, int G> struct NetGeo {
 
 constexpr int EPI_WARPS = 16;             // 4 per TMEM lane quarter
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int TC_THREADS = 64 + EPI_THREADS;   // + producer warp + MMA warp
+constexpr int TC_THREADS = EPI_THREADS + 64;   // + producer warp + MMA warp
+constexpr int WARP_PRODUCER = EPI_WARPS, WARP_MMA = EPI_WARPS + 1;
 
 template <int N, int G>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -209,7 +211,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
         mbar_init(bar_actready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -219,7 +221,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == WARP_PRODUCER) {
         // ===== weight producer: per layer 9 pass-1 stages (two copies) then 9 pass-2 stages (one copy) =====
         if (lane == 0) {
             uint32_t wc = 0;
@@ -244,7 +246,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == WARP_MMA) {
         // ===== MMA issuer: the warp walks the pipeline together, one elected lane issues =====
         {
             uint32_t wc = 0, lc = 0;
@@ -301,10 +303,10 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
             }
         }
     } else {
-        // ===== epilogue warps (8 warps, 256 threads) =====
-        const int et = threadIdx.x - 64;                         // 0..EPI_THREADS-1
+        // ===== epilogue warps =====
+        const int et = threadIdx.x;                              // 0..EPI_THREADS-1
         const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
-        const int tile0 = (warp - 2) >> 2;                       // which tiles: t % 4 == tile0
+        const int tile0 = warp >> 2;                             // which tiles: t % 4 == tile0
         const float* bias_s = reinterpret_cast<const float*>(smem + NG::OFF_BIAS);
         const float* headw_s = reinterpret_cast<const float*>(smem + NG::OFF_HEADW);
         float* pact = reinterpret_cast<float*>(smem + NG::OFF_PACT);
@@ -340,7 +342,9 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                 const bool last = (l == L - 1);
                 const float inv_scale = 1.0f / P.scale[l];
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
-                mbar_wait(bar_accfull, lc & 1);
+                // one lane polls the MMA-completion barrier; the other epilogue warps sleep in the named barrier
+                if (et == 0) mbar_wait(bar_accfull, lc & 1);
+                asm volatile("bar.sync 1, 512;" ::: "memory");
                 tc_fence_after();
                 for (int t = tile0; t < NG::TILES; t += EPI_WARPS / 4) {
                     const int r = t * 128 + quarter * 32 + lane;
@@ -429,8 +433,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
             {
-                const int ew = warp - 2;
-                for (int b = ew; b < G; b += EPI_WARPS) {
+                for (int b = warp; b < G; b += EPI_WARPS) {
                     const int slot = slot0 + b;
                     if (slot >= n_slots) continue;
                     // value head: 3 logits + softmax
@@ -469,7 +472,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == WARP_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512));
     }

@@ -582,10 +582,10 @@ extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t st
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
     e->last_eval_ms = 0.f;
     for (int i = 2; i + 1 < ev; i += 2) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->events[i], e->events[i + 1])); e->last_eval_ms += ms; }
-    int64_t evals = 0; int any_err = 0;
+    int64_t evals = 0, uevals = 0; int any_err = 0;
     for (int g = 0; g < games; g++) {
         const int* gs = e->h_gs + (size_t)g * GS_STRIDE;
-        evals += gs[GS_EVALS];
+        evals += gs[GS_EVALS]; uevals += gs[GS_UEVALS];
         any_err |= gs[GS_ERROR];
         if (!out) continue;
         if (out->move) out->move[g] = gs[GS_LAST_MOVE];
@@ -597,12 +597,12 @@ extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t st
         if (out->score) { float f; memcpy(&f, &gs[GS_SCORE], 4); out->score[g] = f; }
         if (out->error) out->error[g] = gs[GS_ERROR];
     }
-    e->last_eval_slots = evals;
+    e->last_eval_slots = uevals;
     if (out) {
         if (out->action) memcpy(out->action, e->h_action, (size_t)games * e->AP * 2);
         if (out->improved) memcpy(out->improved, e->h_improved, (size_t)games * e->AP * 8);
         if (out->visits) memcpy(out->visits, e->h_visits, (size_t)games * e->AP * 4);
-        if (out->evals) *out->evals = evals;
+        if (out->evals) { out->evals[0] = evals; out->evals[1] = uevals; }
     }
     if (any_err && !(out && out->error)) return fail(TG_ERR_SEARCH, "search error flags set (history/depth/node/queue overflow); pass tg_step_result.error to inspect");
     return TG_OK;

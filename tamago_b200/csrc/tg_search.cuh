@@ -22,7 +22,7 @@ enum : int {
     GS_NLEAF = 20, GS_NUNIQ = 21, GS_SLOT0 = 22, GS_ERROR = 23, GS_DONE = 24, GS_DESC = 25,
     GS_PASSCNT = 26, GS_NMOVES = 27, GS_FINISHED = 28, GS_NEVER_RESIGN = 29, GS_LAST_MOVE = 30,
     GS_ROOT_K = 31, GS_ACTIVE = 32, GS_WINNER = 33, GS_RESIGNED = 34, GS_SCORE = 35, GS_ROOTPASS = 36,
-    GS_LAST_COLOR = 37, GS_EVALS = 38, GS_STRIDE = 48
+    GS_LAST_COLOR = 37, GS_EVALS = 38, GS_UEVALS = 39, GS_STRIDE = 48
 };
 enum : int { ERR_DEPTH = 1, ERR_HISTORY = 2, ERR_NODES = 4, ERR_QUEUE = 8 };
 enum : int { MODE_SH = 0, MODE_PUCT = 1 };
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_root_begin(Dev D)
     const Tree t = tree_of<G::AP>(D.tree, g);
     if (lane == 0) {
         gs[GS_NNODES] = 0; gs[GS_PHASE] = 0; gs[GS_NPHASES] = 0; gs[GS_DONE] = 0; gs[GS_DESC] = 0; gs[GS_ROOTPASS] = 0;
-        gs[GS_ERROR] = 0; gs[GS_EVALS] = 0;
+        gs[GS_ERROR] = 0; gs[GS_EVALS] = 0; gs[GS_UEVALS] = 0;
     }
     __syncwarp();
     const int color = gs[GS_COLOR];
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_backup(Dev D, int use_log
         }
         __syncwarp();
     }
-    if (lane == 0) gs[GS_EVALS] += nl;
+    if (lane == 0) { gs[GS_EVALS] += nl; gs[GS_UEVALS] += gs[GS_NUNIQ]; }
 }
 
 // ---------------------------------------------------------------------------------------------

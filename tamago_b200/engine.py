@@ -126,7 +126,7 @@ class Engine:
         g, s = self.games, self.stride
         r = dict(move=np.zeros(g, np.int32), color=np.zeros(g, np.int32), num_children=np.zeros(g, np.int32),
                  finished=np.zeros(g, np.int32), winner=np.zeros(g, np.int32), resigned=np.zeros(g, np.int32),
-                 score=np.zeros(g, np.float32), error=np.zeros(g, np.int32), evals=np.zeros(1, np.int64))
+                 score=np.zeros(g, np.float32), error=np.zeros(g, np.int32), evals=np.zeros(2, np.int64))
         if full:
             r.update(action=np.zeros((g, s), np.int16), improved=np.zeros((g, s), np.float64), visits=np.zeros((g, s), np.int32))
         sr = _lib.StepResult()
