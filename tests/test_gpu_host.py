@@ -1,0 +1,129 @@
+"""The Python surfaces that stay drop-in on the B200: MCTSTree, selfplay_worker, GoBoard, DualNet."""
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import SearchGolden
+
+pytestmark = pytest.mark.gpu
+
+
+class _HashNet:
+    """stands in for the network object: selects the engine's hash evaluator (tree parity with the goldens)"""
+    def __init__(self):
+        import tamago_b200 as tb
+        self.evaluator = tb.EVAL_HASHNET
+        self.state_dict_np = None
+
+
+def test_mctstree_dropin_matches_reference_golden(golden_dir):
+    from tamago_b200.board.go_board import GoBoard
+    from tamago_b200.board.stone import Stone
+    from tamago_b200.mcts.tree import MCTSTree
+    from tamago_b200.mcts.time_manager import TimeManager, TimeControl
+    sg = SearchGolden(os.path.join(golden_dir, "search_9.npz"))
+    checked = 0
+    for i in range(sg.ncases):
+        meta, nodes, improved = sg.case(i)
+        if meta["batch"] != 1:
+            continue
+        board = GoBoard(9, 7.0, True)
+        board.zobrist_table = sg.zobrist
+        color = Stone.BLACK
+        for p in sg.movelist(meta["pos_index"]):
+            board.put_stone(int(p), color)
+            color = Stone.get_opponent_color(color)
+        tree = MCTSTree(_HashNet(), tree_size=4096, seed=sg.seed)
+        tree._game_counter = meta["pos_index"] - 1          # noise key (seed, game = pos_index, move = board.moves)
+        tm = TimeManager(TimeControl.CONSTANT_PLAYOUT, constant_visits=meta["visits"])
+        before = board.get_move_history()
+        if meta["kind"] == 0:
+            mv = tree.generate_move_with_sequential_halving(board, color, tm, True)
+        else:
+            mv = tree.search_best_move(board, color, tm, {})
+        assert board.get_move_history() == before            # the caller's board is not modified
+        assert mv == meta["move"], (i, meta)
+        root = tree.get_root()
+        assert root.get_num_children() == nodes[0]["k"]
+        assert np.array_equal(root.children_visits, nodes[0]["visits"])
+        assert [root.get_child_move(j) for j in range(root.get_num_children())] == list(nodes[0]["action"])
+        assert tree.num_nodes == len(nodes)
+        if meta["kind"] == 0:
+            np.testing.assert_allclose(root.calculate_improved_policy(), improved, rtol=1e-12)
+        checked += 1
+    assert checked >= 10
+
+
+def test_selfplay_worker_writes_reference_sgf(golden_dir, tmp_path):
+    import tamago_b200 as tb
+    from tamago_b200.selfplay.worker import selfplay_worker
+    g = np.load(os.path.join(golden_dir, "selfplay_9.npz"))
+    ng = len(g["sgf"])
+    for dedup in (False, True):
+        d = tmp_path / f"dedup{int(dedup)}"
+        d.mkdir()
+        n = selfplay_worker(str(d), "/nonexistent/model.bin", list(range(ng)), int(g["size"]), int(g["visits"]), True,
+                            pool_size=ng, dedup=dedup, seed=int(g["seed"]), network=_HashNet(), evaluator=tb.EVAL_HASHNET,
+                            zobrist=g["zobrist"], never_resign_fn=lambda idx: idx % 2 == 0)
+        assert n == len(g["moves"])
+        for k in range(ng):
+            assert (d / f"{k}.sgf").read_text(encoding="utf-8") == str(g["sgf"][k])
+        # resume rule of worker.py:47-48: existing files are skipped
+        assert selfplay_worker(str(d), "/nonexistent/model.bin", list(range(ng)), 9, 16, True, network=_HashNet(),
+                               evaluator=tb.EVAL_HASHNET) == 0
+
+
+def test_selfplay_worker_pool_smaller_than_index_list(tmp_path):
+    """More games than pool slots: finished games are replaced by the next index; all files appear, all parse."""
+    import tamago_b200 as tb
+    from tamago_b200.selfplay.worker import selfplay_worker
+    from tamago_b200.nn.network import DualNet
+    net = DualNet(board_size=9, seed=3)
+    n = selfplay_worker(str(tmp_path), "", list(range(1, 13)), 9, 16, True, pool_size=5, seed=1, network=net)
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 12 and n > 12 * 10
+    for f in files:
+        text = (tmp_path / f).read_text()
+        assert text.startswith("(;FF[4]GM[1]SZ[9]\nAP[TamaGo]") and text.endswith("\n)") and ";B[" in text
+
+
+def test_goboard_queries_match_oracle():
+    from oracle import oracle as orc
+    from tamago_b200.board.go_board import GoBoard
+    import tamago_b200.board.go_board as gb
+    rs = np.random.RandomState(8)
+    zob = orc.default_zobrist(9)
+    b = GoBoard(9, 7.0, True)
+    ob = orc.OracleBoard(9, 7.0, True, zob)
+    gb._rule_engine(9, True).set_zobrist(zob)
+    color = 1
+    for i in range(60):
+        cand = ob.candidates(color)
+        pos = int(rs.choice(cand[:-1])) if len(cand) > 1 else 0
+        b.put_stone(pos, color); ob.put_stone(pos, color); color = 3 - color
+        if i % 10 == 9:
+            legal = [p for p in ob.onboard_pos if ob.is_legal(p, color)]
+            assert b.get_all_legal_pos(color) == legal
+            assert b.get_candidates(color) == list(ob.candidates(color))
+            assert b.count_score() == ob.count_score() and b.get_hash() == ob.hash
+            assert b.get_board_data() == [int(ob.state()["color"][p]) for p in ob.onboard_pos]
+
+
+def test_dualnet_handle_inference_matches_oracle():
+    import torch
+    from oracle.dualnet_ref import DualNetRef
+    from tamago_b200.nn.network import DualNet
+    net = DualNet(board_size=9, seed=5)
+    ref = DualNetRef(net.state_dict_np, 9)
+    rs = np.random.RandomState(0)
+    x = np.zeros((7, 6, 9, 9), np.float32)
+    cls = rs.randint(0, 3, (7, 9, 9))
+    for c in range(3):
+        x[:, c] = (cls == c)
+    x[:, 5] = 1.0
+    pol, val = net.inference(torch.from_numpy(x))
+    rp, rv = ref.evaluator()(x, False)
+    assert isinstance(pol, torch.Tensor) and np.abs(pol.numpy() - rp).max() <= 1e-4 and np.abs(val.numpy() - rv).max() <= 1e-4
+    lg, _ = net.inference_with_policy_logits(torch.from_numpy(x))
+    assert np.abs(lg.numpy() - ref.evaluator()(x, True)[0]).max() <= 1e-4
