@@ -11,12 +11,15 @@
 //   * fp32-grade accuracy from fp16 operands: x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, three MMAs accumulating
 //     into the same fp32 TMEM tile (the reference net is fp32, tolerance 1e-4).  Two details matter for the
 //     last digit: x_lo is stored scaled by 2^11 (against a 2^-11-scaled copy of w_hi) so it never becomes an
-//     fp16 subnormal, and each layer runs the two small correction terms for all nine taps FIRST and the big
-//     x_hi*w_hi terms LAST -- the tensor core truncates when it adds into the accumulator, and the truncation
-//     error scales with the accumulator's magnitude at that moment;
-//   * BatchNorm (eval mode) is folded into the weights/bias on the host; the residual skip never touches
-//     memory: the block input is parked in a second TMEM region and added in conv2's epilogue;
-//   * weights stream from L2 through a 4-stage cp.async.bulk/mbarrier ring (pass 1: 16 KB per tap, pass 2: 8 KB);
+//     fp16 subnormal, and the big x_hi*w_hi terms and the two small correction terms accumulate in SEPARATE
+//     TMEM accumulators that are only added in the epilogue -- the tensor core truncates when it adds into the
+//     accumulator, and that error scales with the accumulator's magnitude;
+//   * shared-memory operand traffic bounds the MMA rate (a 128x16 A tile is 4 KB per instruction), so x_hi is
+//     multiplied against [w_hi | w_lo] stacked to N=128 in ONE instruction (columns 0..63 -> main accumulator,
+//     64..127 -> small accumulator); only x_lo needs a second, N=64 instruction;
+//   * BatchNorm (eval mode) is folded into the weights/bias on the host; the residual skip goes through a
+//     per-CTA fp32 scratch that stays L2 resident (128 KB per CTA) and is added in conv2's epilogue;
+//   * weights stream from L2 through a 3-stage cp.async.bulk/mbarrier ring (24 KB per tap);
 //   * warp roles: 0..15 = epilogue (TMEM -> bias/ReLU/split -> smem) and heads, 16 = weight producer, 17 = MMA issuer
 //     (the highest warp id: it must never wait for an issue slot behind the epilogue warps).
 //
@@ -29,18 +32,20 @@
 namespace tg {
 
 constexpr int NET_F = 64;                 // filters (dual_net.py:25)
-constexpr int W_STAGES = 4;
-constexpr int W_STAGE_BYTES = 2 * 8 * 64 * 16;      // two operand copies, 8 chunks x 64 oc x 16 B = 16 KB
-constexpr int W_COPY_BYTES = 8 * 64 * 16;           // one 64x64 fp16 weight tile (8 KB)
-constexpr int W_STEM_COPY_BYTES = 2 * 64 * 16;      // one 64x16 stem tile (2 KB)
-constexpr int W_LAYER_HALVES = 9 * 3 * (W_COPY_BYTES / 2);   // fp16 elements per 64->64 layer (3 copies per tap)
+constexpr int W_STAGES = 3;
+constexpr int W_HS_BYTES = 8 * 64 * 16;             // w_hi * 2^-11 as a 64 x 64 B tile (8 KB)
+constexpr int W_HL_BYTES = 8 * 128 * 16;            // [w_hi | w_lo] as a 128 x 64 B tile (16 KB)
+constexpr int W_STAGE_BYTES = W_HS_BYTES + W_HL_BYTES;       // one tap: 24 KB
+constexpr int W_STEM_TAP_BYTES = 2 * 128 * 16;      // stem tap: [w_hi | w_lo] 128 x 16 (4 KB)
+constexpr int W_LAYER_HALVES = 9 * (W_STAGE_BYTES / 2);      // fp16 elements per 64->64 layer
+constexpr int SKIP_FLOATS_PER_CTA = 16 * 512 * 4;
 constexpr float LO_SCALE = 2048.0f;                 // x_lo is stored as x_lo * 2^11
 
 struct NetDev {
     int blocks;                  // residual blocks (dual_net.py:26)
     // tensor-core operands
-    const __half* w_stem;        // pass 1: [9 taps][w_lo][2 chunks][64 oc][8 ic], then pass 2: [9 taps][w_hi][2][64][8]
-    const __half* w_conv;        // per layer: pass 1 [9 taps][w_hi*2^-11, w_lo][8 chunks][64 oc][8 ic], pass 2 [9 taps][w_hi][8][64][8]
+    const __half* w_stem;        // [9 taps][2 chunks][128 rows: w_hi oc 0..63, w_lo oc 0..63][8 ic]
+    const __half* w_conv;        // per layer [9 taps]{ [8 chunks][64 oc][8 ic] of w_hi*2^-11 ; [8 chunks][128 rows: w_hi, w_lo][8 ic] }
     const float* bias;           // [1+2*blocks][64]   BN-folded bias
     const float* scale;          // [1+2*blocks]       power-of-two weight scale of the layer
     // heads (fp32)
@@ -53,6 +58,8 @@ struct NetDev {
     // fp32 CUDA-core path
     const float* w32_stem;       // [6 ic][9][64 oc]
     const float* w32_conv;       // [2*blocks][64 ic][9][64 oc]
+    float* skip;                 // [CTAs][16 channel quads][512 rows][4] fp32 residual scratch (L2 resident)
+    long long* dbg;              // optional timing probe (development): [64] clock64 stamps of CTA 0, first group
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -121,6 +128,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor: D=F32, A=B=F16, both K-major, M=128, N=64 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t IDESC_F16_M128_N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 #define TG_TMEM_LD32(taddr, v) \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " \
@@ -130,6 +138,12 @@ constexpr uint32_t IDESC_F16_M128_N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u 
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
+        : "r"(taddr) : "memory")
+#define TG_TMEM_LD16(taddr, v) \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 " \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
         : "r"(taddr) : "memory")
 #define TG_TMEM_ST32(taddr, v) \
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], " \
@@ -156,8 +170,8 @@ template <int N, int G> struct NetGeo {
     static constexpr int R = ((L0 + TILES * 128 + PITCH + 1 + 7) / 8) * 8;   // rows allocated per chunk plane
     static constexpr int PLANE_BYTES = R * 16;                   // one 8-channel chunk plane
     static constexpr int ACT_BYTES = 8 * PLANE_BYTES;            // one fp16 copy (hi or lo) of the activations
-    static constexpr int COL_S = 0, COL_A = 256;                 // TMEM regions: S (skip / stem / conv2), A (conv1)
-    static_assert(TILES * 64 <= 256, "group too large for the two TMEM regions");
+    // TMEM: tile t owns columns [128 t, 128 t + 128): main accumulator (x_hi w_hi) | small accumulator (corrections)
+    static_assert(TILES * 128 <= 512 && TILES <= 4, "group too large for TMEM");
     // shared memory carve-up
     static constexpr int OFF_HI = 0;
     static constexpr int OFF_LO = OFF_HI + ACT_BYTES;
@@ -168,7 +182,7 @@ template <int N, int G> struct NetGeo {
     static constexpr int OFF_VACT = OFF_PACT + G * 2 * NN * 4;                 // [G][NN]
     static constexpr int OFF_LOGIT = OFF_VACT + G * NN * 4;                    // [G][A]
     static constexpr int OFF_BAR = (OFF_LOGIT + G * A * 4 + 15) & ~15;         // mbarriers + tmem address
-    static constexpr int SMEM_BYTES = OFF_BAR + 128;
+    static constexpr int SMEM_BYTES = OFF_BAR + 192;
 };
 
 constexpr int EPI_WARPS = 16;             // 4 per TMEM lane quarter
@@ -191,9 +205,9 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NG::OFF_BAR);
     const uint32_t bar_wfull = smem_u32(bars + 0);           // [W_STAGES]
     const uint32_t bar_wempty = smem_u32(bars + W_STAGES);   // [W_STAGES]
-    const uint32_t bar_accfull = smem_u32(bars + 2 * W_STAGES);
-    const uint32_t bar_actready = smem_u32(bars + 2 * W_STAGES + 1);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * W_STAGES + 2);
+    const uint32_t bar_accfull = smem_u32(bars + 2 * W_STAGES);          // [4] per tile: accumulators of the layer complete
+    const uint32_t bar_actready = smem_u32(bars + 2 * W_STAGES + 4);     // [4] per tile: next layer's input rows written
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * W_STAGES + 8);
 
     // ---- one-time setup -------------------------------------------------------------------------
     {   // zero both activation copies once (halo rows stay zero for the lifetime of the CTA)
@@ -207,8 +221,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < W_STAGES; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 1); }
-        mbar_init(bar_accfull, 1);
-        mbar_init(bar_actready, 1);
+        for (int t = 0; t < 4; t++) { mbar_init(bar_accfull + 8 * t, 1); mbar_init(bar_actready + 8 * t, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_MMA) {
@@ -222,24 +235,17 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == WARP_PRODUCER) {
-        // ===== weight producer: per layer 9 pass-1 stages (two copies) then 9 pass-2 stages (one copy) =====
+        // ===== weight producer: one tap per stage =====
         if (lane == 0) {
             uint32_t wc = 0;
             for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
                 for (int l = 0; l < L; l++) {
-                    for (int it = 0; it < 18; it++, wc++) {
+                    for (int tap = 0; tap < 9; tap++, wc++) {
                         const uint32_t st = wc % W_STAGES, par = (wc / W_STAGES) & 1;
                         mbar_wait(bar_wempty + 8 * st, par ^ 1);
-                        const int pass = it / 9, tap = it % 9;
-                        uint32_t bytes; const __half* src;
-                        if (l == 0) {
-                            bytes = W_STEM_COPY_BYTES;
-                            src = P.w_stem + (size_t)(pass * 9 + tap) * (W_STEM_COPY_BYTES / 2);
-                        } else {
-                            const __half* lw = P.w_conv + (size_t)(l - 1) * W_LAYER_HALVES;
-                            bytes = pass == 0 ? 2 * W_COPY_BYTES : W_COPY_BYTES;
-                            src = pass == 0 ? lw + (size_t)tap * W_COPY_BYTES : lw + (size_t)9 * W_COPY_BYTES + (size_t)tap * (W_COPY_BYTES / 2);
-                        }
+                        const uint32_t bytes = l == 0 ? W_STEM_TAP_BYTES : W_STAGE_BYTES;
+                        const __half* src = l == 0 ? P.w_stem + (size_t)tap * (W_STEM_TAP_BYTES / 2)
+                                                   : P.w_conv + (size_t)(l - 1) * W_LAYER_HALVES + (size_t)tap * (W_STAGE_BYTES / 2);
                         mbar_arrive_expect_tx(bar_wfull + 8 * st, bytes);
                         bulk_g2s(smem_u32(smem + NG::OFF_W + st * W_STAGE_BYTES), src, bytes, bar_wfull + 8 * st);
                     }
@@ -253,52 +259,53 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
             // descriptor low words: (address >> 4) | (LBO >> 4) << 16; high word: (SBO >> 4) | version 1
             const uint32_t a_hi0 = ((smem_u32(smem + NG::OFF_HI) >> 4) & 0x3FFFu) | ((uint32_t)(NG::PLANE_BYTES >> 4) << 16);
             const uint32_t a_lo0 = ((smem_u32(smem + NG::OFF_LO) >> 4) & 0x3FFFu) | ((uint32_t)(NG::PLANE_BYTES >> 4) << 16);
-            const uint32_t w0 = ((smem_u32(smem + NG::OFF_W) >> 4) & 0x3FFFu) | ((1024u >> 4) << 16);
+            const uint32_t w_addr16 = (smem_u32(smem + NG::OFF_W) >> 4) & 0x3FFFu;
+            constexpr uint32_t LBO_HS = (1024u >> 4) << 16;          // 64-row weight tile: K chunks 1 KB apart
+            constexpr uint32_t LBO_HL = (2048u >> 4) << 16;          // 128-row weight tile: K chunks 2 KB apart
             constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
             constexpr uint32_t KS16 = 2 * NG::PLANE_BYTES / 16;      // A advance per K=16 step, in 16-byte units
             for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
                 for (int l = 0; l < L; l++, lc++) {
-                    mbar_wait(bar_actready, lc & 1);
-                    tc_fence_after();
-                    // pass 1: the small correction terms of all taps; pass 2: the x_hi*w_hi terms (see file header)
-                    for (int it = 0; it < 18; it++, wc++) {
+                    // Tiles are pipelined against the epilogue: a tile's first-tap MMAs wait only for the epilogue of the
+                    // tiles they read (t-1, t), and a tile's accumulators are released right after its last-tap MMAs.
+                    // Safe with in-place activations because taps are issued in order: the last tap (+1,+1) of later
+                    // tiles only reads rows beyond tile t, and every earlier tap of every tile has completed by then.
+                    for (int tap = 0; tap < 9; tap++, wc++) {
                         const uint32_t st = wc % W_STAGES, par = (wc / W_STAGES) & 1;
                         mbar_wait(bar_wfull + 8 * st, par);
                         tc_fence_after();
-                        const int tap = it >= 9 ? it - 9 : it;
                         const uint32_t row16 = (uint32_t)(NG::L0 + (tap / 3 - 1) * NG::PITCH + (tap % 3 - 1));
                         const uint32_t ah = a_hi0 + row16, al = a_lo0 + row16;
-                        const uint32_t wb = w0 + st * (W_STAGE_BYTES / 16);
-                        const uint32_t d0 = tmem_base + NG::COL_A;
-                        if (elect_one()) {
-                        if (l == 0) {
-                            // K = 16: 6 input planes + zero padding, exact in fp16 -> only the weight is split
+                        const uint32_t wst = w_addr16 + st * (W_STAGE_BYTES / 16);
+                        const uint32_t whs = wst | LBO_HS, whl = (wst + W_HS_BYTES / 16) | LBO_HL;
 #pragma unroll
-                            for (int t = 0; t < NG::TILES; t++)
-                                tc_mma_f16_w(d0 + t * 64, ah + t * 128, wb, DESC_HI, IDESC_F16_M128_N64, it > 0);
-                        } else if (it < 9) {
+                        for (int t = 0; t < NG::TILES; t++) {
+                            if (tap == 0) {
+                                mbar_wait(bar_actready + 8 * t, lc & 1);
+                                tc_fence_after();
+                                if (P.dbg && blockIdx.x == 0 && lc < 14 && lane == 0 && t == 0) P.dbg[lc * 4 + 0] = clock64();
+                            }
+                            if (elect_one()) {
+                                if (l == 0) {
+                                    // K = 16: 6 input planes + zero padding, exact in fp16 -> only the weight is split
+                                    tc_mma_f16_w(tmem_base + t * 128, ah + t * 128, wst | LBO_HL, DESC_HI, IDESC_F16_M128_N128, tap > 0);
+                                } else {
 #pragma unroll
-                            for (int t = 0; t < NG::TILES; t++) {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ks++) {
-                                    tc_mma_f16_w(d0 + t * 64, al + t * 128 + ks * KS16, wb + ks * 128, DESC_HI, IDESC_F16_M128_N64,
-                                                 (it > 0 || ks > 0) ? 1u : 0u);                          // x_lo*2^11 . w_hi*2^-11
-                                    tc_mma_f16_w(d0 + t * 64, ah + t * 128 + ks * KS16, wb + 512 + ks * 128, DESC_HI, IDESC_F16_M128_N64, 1u);   // x_hi . w_lo
+                                    for (int ks = 0; ks < 4; ks++) {
+                                        // x_hi . [w_hi | w_lo] -> main | small  (initialises both at the first step)
+                                        tc_mma_f16_w(tmem_base + t * 128, ah + t * 128 + ks * KS16, whl + ks * 256, DESC_HI, IDESC_F16_M128_N128,
+                                                     (tap > 0 || ks > 0) ? 1u : 0u);
+                                        // (x_lo * 2^11) . (w_hi * 2^-11) -> small
+                                        tc_mma_f16_w(tmem_base + t * 128 + 64, al + t * 128 + ks * KS16, whs + ks * 128, DESC_HI, IDESC_F16_M128_N64, 1u);
+                                    }
                                 }
+                                if (tap == 8) tc_commit(bar_accfull + 8 * t);             // this tile's accumulators are complete
+                                if (t == NG::TILES - 1) tc_commit(bar_wempty + 8 * st);   // stage is free once these MMAs have read it
                             }
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < NG::TILES; t++) {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ks++)
-                                    tc_mma_f16_w(d0 + t * 64, ah + t * 128 + ks * KS16, wb + ks * 128, DESC_HI, IDESC_F16_M128_N64, 1u);         // x_hi . w_hi
-                            }
+                            __syncwarp();
                         }
-                        tc_commit(bar_wempty + 8 * st);          // stage is free once these MMAs have read it
-                        if (it == 17) tc_commit(bar_accfull);    // layer finished: accumulators complete
-                        }
-                        __syncwarp();
                     }
+                    if (P.dbg && blockIdx.x == 0 && lc < 14 && lane == 0) P.dbg[lc * 4 + 1] = clock64();
                 }
             }
         }
@@ -316,6 +323,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
         for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
             const int slot0 = grp * G;
             // ---- input planes -> fp16 rows (channels 0..5; 6..15 zero) ----
+            static_assert(NG::TILES * 128 == EPI_THREADS, "one epilogue thread per row");
             for (int r = et; r < NG::TILES * 128; r += EPI_THREADS) {
                 const int b = r / NG::BR, q = r - b * NG::BR;
                 const int y = q / NG::PITCH - 1, x = q - (y + 1) * NG::PITCH;
@@ -333,8 +341,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
             }
             fence_proxy_async();
             tc_fence_before();
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            if (et == 0) mbar_arrive(bar_actready);
+            mbar_arrive(bar_actready + 8 * tile0);               // thread et wrote row et, a row of tile et / 128
 
             for (int l = 0; l < L; l++, lc++) {
                 const bool is_conv1 = (l >= 1) && ((l - 1) % 2 == 0);
@@ -342,10 +349,11 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                 const bool last = (l == L - 1);
                 const float inv_scale = 1.0f / P.scale[l];
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
-                // one lane polls the MMA-completion barrier; the other epilogue warps sleep in the named barrier
-                if (et == 0) mbar_wait(bar_accfull, lc & 1);
-                asm volatile("bar.sync 1, 512;" ::: "memory");
+                // one lane per warp polls its tile's MMA-completion barrier
+                if (lane == 0) mbar_wait(bar_accfull + 8 * tile0, lc & 1);
+                __syncwarp();
                 tc_fence_after();
+                if (P.dbg && blockIdx.x == 0 && lc < 14 && et == 0) P.dbg[lc * 4 + 2] = clock64();
                 for (int t = tile0; t < NG::TILES; t += EPI_WARPS / 4) {
                     const int r = t * 128 + quarter * 32 + lane;
                     const int b = r / NG::BR, q = r - b * NG::BR;
@@ -353,33 +361,41 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                     const bool interior = (b < G) && (y >= 0) && (x < N);
                     const float cap = interior ? 60000.0f : 0.0f;                      // halo rows stay zero; fp16 range guard
                     hp0 = 0.f; hp1 = 0.f; hv = 0.f;
+                    float* skip_row = P.skip + (size_t)blockIdx.x * SKIP_FLOATS_PER_CTA + (size_t)r * 4;   // [quad][row][4]
 #pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        uint32_t v[32];
-                        const uint32_t lane_col = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 64 + c0;
-                        TG_TMEM_LD32(lane_col + NG::COL_A, v);
+                    for (int c0 = 0; c0 < 64; c0 += 16) {
+                        uint32_t v[16], w[16];
+                        float4 sk[4];
+                        if (is_conv2) {                                                 // issue the skip loads early (L2)
+#pragma unroll
+                            for (int qd = 0; qd < 4; qd++) sk[qd] = *reinterpret_cast<const float4*>(skip_row + (size_t)(c0 / 4 + qd) * 2048);
+                        }
+                        const uint32_t lane_col = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 128 + c0;
+                        TG_TMEM_LD16(lane_col, v);                                      // main accumulator: x_hi . w_hi
+                        TG_TMEM_LD16(lane_col + 64, w);                                 // small accumulator: corrections
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        float o[32];
+                        float o[16];
 #pragma unroll
-                        for (int j = 0; j < 32; j++) o[j] = fmaf(__uint_as_float(v[j]), inv_scale, bias_s[l * 64 + c0 + j]);
+                        for (int j = 0; j < 16; j++)
+                            o[j] = fmaf(__uint_as_float(v[j]) + __uint_as_float(w[j]), inv_scale, bias_s[l * 64 + c0 + j]);
                         if (is_conv2) {                                                 // res_block.py:39: relu(input + hidden_2)
-                            TG_TMEM_LD32(lane_col + NG::COL_S, v);
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                            for (int j = 0; j < 32; j++) o[j] += __uint_as_float(v[j]);
+                            for (int qd = 0; qd < 4; qd++) {
+                                o[qd * 4 + 0] += sk[qd].x; o[qd * 4 + 1] += sk[qd].y; o[qd * 4 + 2] += sk[qd].z; o[qd * 4 + 3] += sk[qd].w;
+                            }
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; j++) o[j] = fminf(fmaxf(o[j], 0.0f), cap);   // ReLU
+                        for (int j = 0; j < 16; j++) o[j] = fminf(fmaxf(o[j], 0.0f), cap);   // ReLU
                         if (last) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) {
+                            for (int j = 0; j < 16; j++) {
                                 hp0 = fmaf(o[j], headw_s[c0 + j], hp0);
                                 hp1 = fmaf(o[j], headw_s[64 + c0 + j], hp1);
                                 hv = fmaf(o[j], headw_s[128 + c0 + j], hv);
                             }
                         } else {
 #pragma unroll
-                            for (int kk = 0; kk < 4; kk++) {
+                            for (int kk = 0; kk < 2; kk++) {
                                 uint32_t ph[4], pl[4];
 #pragma unroll
                                 for (int e = 0; e < 4; e++) {
@@ -396,8 +412,9 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                             }
                             if (!is_conv1) {                                            // park the block input for the next skip
 #pragma unroll
-                                for (int j = 0; j < 32; j++) v[j] = __float_as_uint(o[j]);
-                                TG_TMEM_ST32(lane_col + NG::COL_S, v);
+                                for (int qd = 0; qd < 4; qd++)
+                                    *reinterpret_cast<float4*>(skip_row + (size_t)(c0 / 4 + qd) * 2048) =
+                                        make_float4(o[qd * 4], o[qd * 4 + 1], o[qd * 4 + 2], o[qd * 4 + 3]);
                             }
                         }
                     }
@@ -409,12 +426,11 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                     }
                 }
                 if (!last) {
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     fence_proxy_async();
                     tc_fence_before();
-                    asm volatile("bar.sync 1, 512;" ::: "memory");
-                    if (et == 0) mbar_arrive(bar_actready);
+                    mbar_arrive(bar_actready + 8 * tile0);
                 }
+                if (P.dbg && blockIdx.x == 0 && lc < 14 && et == 0) P.dbg[lc * 4 + 3] = clock64();
             }
             // ---- heads: FC layers + softmax (policy_head.py:37-40, value_head.py:38-40, dual_net.py:81-106) ----
             tc_fence_before();

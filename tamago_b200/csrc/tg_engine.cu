@@ -115,6 +115,10 @@ template <int BN> static int setup_kernel_attrs()
     CK(cudaFuncSetAttribute(k_play<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_snapshot_roots<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_conv3x3_simt<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * (BN + 2) * (BN + 2) * 4));
+    // the search kernels keep whole boards in shared memory: prefer the largest carve-out so that more games are resident
+    CK(cudaFuncSetAttribute(k_root_begin<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_descend_sh<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return 0;
 }
 template <int BN, int G> static int setup_tc_attr()
@@ -326,8 +330,8 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
         for (int c = 0; c < 2; c++)
             fold(1 + 2 * b + c, w->block_conv_w + ((size_t)b * 2 + c) * 64 * 64 * 9, 64, w->block_bn + ((size_t)b * 2 + c) * 4 * 64, w->block_bn_eps);
 
-    const size_t stem_copy = (size_t)W_STEM_COPY_BYTES / 2, conv_copy = (size_t)W_COPY_BYTES / 2;
-    std::vector<__half> w_stem(18 * stem_copy), w_conv((size_t)(L - 1) * W_LAYER_HALVES);
+    const size_t stem_tap = (size_t)W_STEM_TAP_BYTES / 2, conv_tap = (size_t)W_STAGE_BYTES / 2, hs_halves = (size_t)W_HS_BYTES / 2;
+    std::vector<__half> w_stem(9 * stem_tap), w_conv((size_t)(L - 1) * W_LAYER_HALVES);
     std::vector<float> w32_stem((size_t)6 * 9 * 64), w32_conv((size_t)(L - 1) * 64 * 9 * 64);
     for (int l = 0; l < L; l++) {
         const int cin = l == 0 ? 6 : 64, chunks = l == 0 ? 2 : 8;
@@ -347,14 +351,15 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
                     const __half hi = __float2half_rn((float)vs);
                     const __half lo = __float2half_rn((float)(vs - (double)__half2float(hi)));
                     const __half his = __float2half_rn(__half2float(hi) / LO_SCALE);          // pairs with x_lo * 2^11
-                    const size_t within = ((size_t)(ic / 8) * 64 + oc) * 8 + (ic % 8);
+                    // [chunk][row][8]: the stacked tile has 128 rows per chunk (w_hi rows 0..63, w_lo rows 64..127)
+                    const size_t hl_hi = ((size_t)(ic / 8) * 128 + oc) * 8 + (ic % 8), hl_lo = hl_hi + 64 * 8;
                     if (l == 0) {
-                        lw[(size_t)tap * stem_copy + within] = lo;                             // pass 1
-                        lw[(size_t)(9 + tap) * stem_copy + within] = hi;                       // pass 2
+                        lw[(size_t)tap * stem_tap + hl_hi] = hi;
+                        lw[(size_t)tap * stem_tap + hl_lo] = lo;
                     } else {
-                        lw[(size_t)tap * 2 * conv_copy + within] = his;                        // pass 1, copy 0
-                        lw[(size_t)tap * 2 * conv_copy + conv_copy + within] = lo;             // pass 1, copy 1
-                        lw[(size_t)18 * conv_copy + (size_t)tap * conv_copy + within] = hi;    // pass 2
+                        lw[(size_t)tap * conv_tap + ((size_t)(ic / 8) * 64 + oc) * 8 + (ic % 8)] = his;
+                        lw[(size_t)tap * conv_tap + hs_halves + hl_hi] = hi;
+                        lw[(size_t)tap * conv_tap + hs_halves + hl_lo] = lo;
                     }
                     if (ic < cin) d32[((size_t)ic * 9 + tap) * 64 + oc] = (float)v;
                 }
@@ -384,6 +389,14 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
         (rc = upload(e, pfc_t, &n.pfc_t)) || (rc = upload(e, pfc_b, &n.pfc_b)) || (rc = upload(e, vfc_w, &n.vfc_w)) ||
         (rc = upload(e, vfc_b, &n.vfc_b)) || (rc = upload(e, w32_stem, &n.w32_stem)) || (rc = upload(e, w32_conv, &n.w32_conv)))
         return rc;
+    {
+        void* q = nullptr;
+        CK(cudaMalloc(&q, (size_t)e->sms * SKIP_FLOATS_PER_CTA * sizeof(float)));
+        CK(cudaMemsetAsync(q, 0, (size_t)e->sms * SKIP_FLOATS_PER_CTA * sizeof(float), e->stream));
+        e->net_allocs.push_back(q);
+        n.skip = reinterpret_cast<float*>(q);
+        n.dbg = nullptr;
+    }
     CK(cudaStreamSynchronize(e->stream));
     e->have_weights = true;
     return TG_OK;
@@ -704,6 +717,30 @@ extern "C" int tg_bench_kernel(tg_engine* e, const char* name, int32_t slots, in
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaEventElapsedTime(ms_out, e->events[0], e->events[1]));
         *ms_out /= (float)iters;
+        return TG_OK;
+    }
+    if (k == "dualnet_dbg") {
+        // development probe: per-layer clock64 stamps of CTA 0 (MMA start, MMA issued, epilogue start, epilogue end)
+        long long* d = nullptr;
+        CK(cudaMalloc(&d, 64 * 8));
+        CK(cudaMemset(d, 0, 64 * 8));
+        CK(cudaMemcpyAsync(e->D.n_slots, &slots, 4, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        NetDev saved = e->net;
+        e->net.dbg = d;
+        int rc = 0;
+        DISPATCH_N(e, rc = launch_net<BN>(e, 1, slots));
+        e->net = saved;
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(e->stream));
+        long long h[64];
+        CK(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        for (int l = 0; l < 14; l++)
+            fprintf(stderr, "layer %2d: mma_issue %7lld  mma_start->epi_start %7lld  epilogue %7lld  epi_end->next_mma_start %7lld\n", l,
+                    h[l * 4 + 1] - h[l * 4 + 0], h[l * 4 + 2] - h[l * 4 + 0], h[l * 4 + 3] - h[l * 4 + 2],
+                    l < 13 ? h[(l + 1) * 4 + 0] - h[l * 4 + 3] : 0LL);
+        *ms_out = 0.f;
         return TG_OK;
     }
     if (k == "planes") {

@@ -62,6 +62,7 @@ template <int N> struct WarpSmem {
     WAnalysis<N> an;
     double s0[Geo<N>::AP];
     double s1[Geo<N>::AP];
+    int16_t memo[Geo<N>::AP];        // sequential halving: root child -> first leaf of this phase that went through it
 };
 
 template <int N> __device__ __forceinline__ BoardPool<N> pool_of(const Dev& D)
@@ -110,30 +111,35 @@ __device__ inline int expand_node(const Dev& D, const Tree& t, int g, int* gs, c
     return idx;
 }
 
-// mcts/batch_data.py:18-27: append a leaf to the game's queue.  With dedup, a leaf reached by the same path as
-// an earlier leaf of this batch shares that leaf's evaluator slot (the position is identical).
+// mcts/batch_data.py:18-27: append a leaf to the game's queue.
+//   dup_of >= 0: the leaf is the same position as queue entry dup_of (same path).  With dedup it shares that entry's
+//   evaluator slot (result-preserving), otherwise it gets its own slot with a copy of the snapshot.
+//   dup_of == -1 && search_dups: look for an identical path among the earlier entries (PUCT batches).
 template <int N>
 __device__ inline void push_leaf(const Dev& D, int g, int* gs, const WBoard<N>& b, const BScal& s, int color,
-                                 const unsigned* cur_path, int plen, int node_index, int lane)
+                                 const unsigned* cur_path, int plen, int node_index, int lane, int dup_of = -1, bool search_dups = false)
 {
     const int i = gs[GS_NLEAF];
     if (i >= D.cap) { if (lane == 0) gs[GS_ERROR] |= ERR_QUEUE; __syncwarp(); return; }
     const size_t q = (size_t)g * D.cap;
-    int slot = -1;
-    if (D.dedup) {
-        for (int j = 0; j < i && slot < 0; j++) {
+    if (dup_of < 0 && search_dups && D.dedup) {
+        for (int j = 0; j < i && dup_of < 0; j++) {
             if (D.path_len[q + j] != plen) continue;
             const unsigned* pj = D.path + (q + j) * D.max_depth;
             bool diff = false;
             for (int d = lane; d < plen; d += 32) diff |= (pj[d] != cur_path[d]);
-            if (!__any_sync(0xffffffffu, diff)) slot = D.leaf_slot[q + j];
+            if (!__any_sync(0xffffffffu, diff)) dup_of = j;
         }
     }
-    int nu = gs[GS_NUNIQ];
-    if (slot < 0) {
-        slot = nu;
-        wb_snapshot<N>(b, s, color, D.hist_pos + (size_t)g * Geo<N>::MAXREC, D.snap + (q + slot) * Snap<N>::BYTES, lane);
-        nu++;
+    int nu = gs[GS_NUNIQ], slot;
+    if (dup_of >= 0 && D.dedup) slot = D.leaf_slot[q + dup_of];
+    else {
+        slot = nu++;
+        uint8_t* dst = D.snap + (q + slot) * Snap<N>::BYTES;
+        if (dup_of >= 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(D.snap + (q + D.leaf_slot[q + dup_of]) * Snap<N>::BYTES);
+            for (int k = lane; k < Snap<N>::BYTES / 16; k += 32) reinterpret_cast<uint4*>(dst)[k] = src[k];
+        } else wb_snapshot<N>(b, s, color, D.hist_pos + (size_t)g * Geo<N>::MAXREC, dst, lane);
     }
     if (lane == 0) {
         D.path_len[q + i] = plen; D.leaf_node[q + i] = node_index; D.leaf_slot[q + i] = slot;
@@ -229,17 +235,38 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_sh(Dev D)
     u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
     int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
     const unsigned move_key = (unsigned)rs.moves;
+    // Inside one phase nothing below the root changes (backups happen at the end of the phase, tree.py:384, and
+    // the non-root rule reads visit counts and value sums only, node.py:349-361), so every descent through a given
+    // root child follows the same path to the same leaf.  The first descent through a child walks the board; later
+    // ones replay its path: same virtual-loss updates, same queue entry (tree.py:387-422), no board work.
+    for (int i = lane; i < G::AP; i += 32) sm.memo[i] = -1;
+    __syncwarp();
     for (int thr = 1; thr <= cnt; thr++) {
         for (int j = 0; j < cons; j++) {
-            wb_copy<N>(sm.scratch, sm.root, lane);                               // tree.py:378
-            BScal s = rs;
-            int color = root_color, cur = 0, plen = 0;
             const int li = gs[GS_NLEAF];
             if (li >= D.cap) { if (lane == 0) gs[GS_ERROR] |= ERR_QUEUE; __syncwarp(); return; }
             unsigned* path = D.path + ((size_t)g * D.cap + li) * D.max_depth;
+            const int first = select_sh_root<G::AP>(t, 0, thr, lane);
+            const int m = sm.memo[first];
+            if (m >= 0) {
+                const size_t qm = (size_t)g * D.cap + m;
+                const int plen = D.path_len[qm];
+                const unsigned* src = D.path + qm * D.max_depth;
+                for (int d = lane; d < plen; d += 32) {
+                    const unsigned e = src[d];
+                    path[d] = e;
+                    const int node = (int)(e >> PATH_NODE_SHIFT), c = (int)(e & ((1u << PATH_NODE_SHIFT) - 1));
+                    t.hdr[(size_t)node * H_STRIDE + H_VL] += 1; t.cvl[(size_t)node * G::AP + c] += 1;   // node.py:76-83
+                }
+                __syncwarp();
+                push_leaf<N>(D, g, gs, sm.scratch, rs, root_color, path, plen, D.leaf_node[qm], lane, m);
+                continue;
+            }
+            wb_copy<N>(sm.scratch, sm.root, lane);                               // tree.py:378
+            BScal s = rs;
+            int color = root_color, cur = 0, plen = 0;
             for (;;) {                                                           // tree.py:387-422
-                const int next = (cur == 0) ? select_sh_root<G::AP>(t, cur, thr, lane)
-                                            : select_sh_node<G::AP>(t, cur, sm.s0, sm.s1, lane);
+                const int next = (cur == 0) ? first : select_sh_node<G::AP>(t, cur, sm.s0, sm.s1, lane);
                 const size_t row = (size_t)cur * G::AP;
                 const int mv = t.action[row + next];
                 if (lane == 0) path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
@@ -250,6 +277,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_sh(Dev D)
                 __syncwarp();
                 if (t.cvis[row + next] < 1) {                                    // :412-416
                     push_leaf<N>(D, g, gs, sm.scratch, s, color, path, plen, t.cidx[row + next], lane);
+                    if (lane == 0) sm.memo[first] = (int16_t)li;
+                    __syncwarp();
                     break;
                 }
                 int ci = t.cidx[row + next];
@@ -334,7 +363,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
                     if (lane == 0) t.cidx[row + next] = ci;
                     __syncwarp();
                 }
-                push_leaf<N>(D, g, gs, sm.scratch, s, color, path, plen, ci, lane);
+                push_leaf<N>(D, g, gs, sm.scratch, s, color, path, plen, ci, lane, -1, true);
                 break;
             }
             cur = t.cidx[row + next];
@@ -397,12 +426,25 @@ __global__ void __launch_bounds__(256) k_planes(Dev D)
         uint4* dst = reinterpret_cast<uint4*>(smem_raw);
         for (int i = threadIdx.x; i < nc * (Snap<N>::BYTES / 16); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
-        const int total = nc * G::PLANES;
         if (slot0 + u0 + nc <= D.slot_cap) {
             float* out = D.planes + (size_t)(slot0 + u0) * G::PLANES;
-            for (int i = threadIdx.x; i < total; i += blockDim.x) {
-                const int u = i / G::PLANES, r = i - u * G::PLANES, p = r / G::NN, idx = r - p * G::NN;
-                out[i] = snap_plane_value<N>(smem_raw + u * Snap<N>::BYTES, p, idx);
+            // one warp per (snapshot, plane) row of N*N floats: index arithmetic once per row, coalesced stores
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            for (int row = warp; row < nc * 6; row += 8) {
+                const int u = row / 6, p = row - u * 6;
+                const uint8_t* sn = smem_raw + u * Snap<N>::BYTES;
+                const int color = sn[3];
+                float* o = out + (size_t)row * G::NN;
+                if (p >= 4) {                                                      // feature.py:39-41, 50-52: constant planes
+                    const float v = p == 5 ? (color == WHITE ? -1.0f : 1.0f) : (sn[2] ? 1.0f : 0.0f);
+                    for (int idx = lane; idx < G::NN; idx += 32) o[idx] = v;
+                } else if (p == 3) {                                               // :43-46 previous move
+                    const int pidx = *reinterpret_cast<const int16_t*>(sn);
+                    for (int idx = lane; idx < G::NN; idx += 32) o[idx] = idx == pidx ? 1.0f : 0.0f;
+                } else {                                                           // :24-31 empty / own / opponent
+                    const int want = (color == WHITE && p != 0) ? 3 - p : p;
+                    for (int idx = lane; idx < G::NN; idx += 32) o[idx] = sn[Snap<N>::HDR + idx] == want ? 1.0f : 0.0f;
+                }
             }
         }
         __syncthreads();
