@@ -89,3 +89,23 @@ def test_kernels_match_fp64_reference_on_large_ragged_batch(golden_dir, size):
         dl, dv = np.abs(logits - ref_logits).max(), np.abs(val - ref_val).max()
         print(f"size {size} {name}: max |dlogit| {dl:.3e}, |dvalue| {dv:.3e} vs fp64")
         assert np.isfinite(logits).all() and dl <= TOL and dv <= TOL
+
+
+def test_13x13_tensor_core_kernel_matches_fp64():
+    """13x13 (two boards per CTA group): no reference golden exists for this size, so the check is the fp64 torch evaluation."""
+    import tamago_b200 as tb
+    size, n = 13, 157
+    rs = np.random.RandomState(13)
+    cls = rs.randint(0, 3, (n, size, size))
+    x = np.zeros((n, 6, size, size), np.float32)
+    for c in range(3):
+        x[:, c] = (cls == c)
+    x[:, 5] = np.where(rs.rand(n) < 0.5, 1.0, -1.0)[:, None, None]
+    sd = _weights(size, 77)
+    sd["policy_head.fc_layer.weight"] = (sd["policy_head.fc_layer.weight"] * 0.3).astype(np.float32)
+    ref_logits, ref_val = _torch_dualnet_f64(sd, x, size)
+    e = tb.Engine(board_size=size, games=8, max_visits=32, evaluator=tb.EVAL_DUALNET_TC)
+    e.load_state_dict(sd)
+    logits, val = e.forward(x, use_logit=True)
+    e.close()
+    assert np.abs(logits - ref_logits).max() <= TOL and np.abs(val - ref_val).max() <= TOL
