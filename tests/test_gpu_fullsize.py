@@ -68,7 +68,8 @@ def test_c4_19x19_1024_games_puct400_properties():
             assert root["node_visits"] == root["children_visits"].sum() and root["virtual_loss"] == 0
             assert (root["children_virtual_loss"] == 0).all()
             assert e.tree_size(g) <= visits + 2
-            assert abs(root["children_policy"].sum() - 1.0) < 1e-4               # PUCT roots carry the softmax policy
+            psum = root["children_policy"].sum()     # PUCT roots carry the softmax policy of their candidates
+            assert 0.9 < psum <= 1.0 + 1e-4          # (non-candidate points are dropped, so the sum is <= 1)
     e.close()
 
 
