@@ -391,6 +391,34 @@ def gen_dualnet(size, seed, board_npz, out):
     print(f"dualnet golden: {planes.shape[0]} positions -> {out}")
 
 
+def gen_rldata(size, selfplay_npz, out):
+    """nn/data_generator.py:89-149 on the golden self-play SGFs (BATCH_SIZE patched to 8 so that 24 samples are written)."""
+    import tempfile
+    import nn.data_generator as dg
+    g = np.load(selfplay_npz)
+    tmp = tempfile.mkdtemp()
+    kdir = os.path.join(tmp, "kifu"); os.makedirs(kdir); os.makedirs(os.path.join(tmp, "data"))
+    for i, text in enumerate(g["sgf"]):
+        open(os.path.join(kdir, f"{i}.sgf"), "w", encoding="utf-8").write(str(text))
+    order = []
+    orig_shuffle = random.shuffle
+
+    def shuffle(lst):
+        lst.sort()
+        orig_shuffle(lst)
+        order.extend(int(os.path.basename(p).split(".")[0]) for p in lst)
+    dg.random.shuffle = shuffle
+    dg.BATCH_SIZE = 8
+    random.seed(4242); np.random.seed(4242)
+    dg.generate_reinforcement_learning_data(tmp, [kdir], size)
+    dg.random.shuffle = orig_shuffle
+    d = np.load(os.path.join(tmp, "data", "rl_data_0.npz"))
+    np.savez_compressed(out, size=size, seed=4242, order=np.array(order), input=d["input"], policy=d["policy"],
+                        value=d["value"], kifu_count=d["kifu_count"])
+    shutil.rmtree(tmp)
+    print(f"rl data golden: {len(d['value'])} samples, order {order} -> {out}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=9)
@@ -418,6 +446,8 @@ def main():
             gen_search(N, 77, os.path.join(HERE, f"search_{N}.npz"), [50], [(40, 1)])
     if want("selfplay") and N == 9:
         gen_selfplay(N, 5, os.path.join(HERE, "selfplay_9.npz"), visits=16, n_games=3)
+    if want("rldata") and N == 9:
+        gen_rldata(N, os.path.join(HERE, "selfplay_9.npz"), os.path.join(HERE, "rldata_9.npz"))
     if want("dualnet"):
         gen_dualnet(N, 31337, os.path.join(HERE, f"board_{N}.npz"), os.path.join(HERE, f"dualnet_{N}.npz"))
 
