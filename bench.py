@@ -115,6 +115,11 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    try:                                    # one torch-importing process per core: stay inside the host's free memory
+        import psutil
+        cores = max(1, min(cores, int(psutil.virtual_memory().available // (1 << 30))))
+    except Exception:
+        pass
     mpp = max(1, a.ref_moves)
     vals, walls = [], []
     for _ in range(a.warmup if a.warmup < 2 else 1):
@@ -270,7 +275,9 @@ def run_ours(a):
         "gpu_launches": launches_all,
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "k_dualnet_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
+                     "frac": achieved / peak, "traffic": 2391.0 * evals / max(1, a.steps * 5),
+                     "traffic_source": "profiles/r01_dualnet_tc.md: 235.0 MB DRAM read+write for a 98.3 k-evaluation launch = 2391 B per evaluation (algorithmic 2284 B: planes in, policy/value out), scaled to this run's mean evaluations per launch (5 launches per step)",
+                     "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                      "evals_per_step": evals / a.steps, "flop_per_eval": flop, "kernel_ms_per_step": eval_ms / a.steps,
                      "kernel_share_of_step": eval_ms / dev_ms if dev_ms else None,
                      "note": "algorithmic FLOP (72.28 MFLOP/eval at 9x9); the kernel executes 3 fp16 MMAs per product for fp32-grade accuracy"},

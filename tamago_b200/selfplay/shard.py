@@ -32,3 +32,32 @@ def reduce_counters(moves, seconds, device=None):
     s = t.clone(); dist.all_reduce(s, op=dist.ReduceOp.SUM)
     m = t.clone(); dist.all_reduce(m, op=dist.ReduceOp.MAX)
     return s[0].item(), m[1].item()
+
+
+def gather_training_arrays(arrays, dst=0):
+    """Optional collection of finished training records on one rank (the reference's workers meet in a shared
+    directory instead): `arrays` is a dict of numpy arrays whose first dimension is the local sample count.  Uses one
+    all_gather of the counts and one padded all_gather per array (NCCL when the tensors live on a GPU, gloo on the CPU)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return arrays
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    n_local = len(next(iter(arrays.values())))
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n_local], dtype=torch.int64, device=dev))
+    counts = [int(c.item()) for c in counts]
+    nmax = max(counts + [1])
+    out = {}
+    for key, a in arrays.items():
+        a = np.ascontiguousarray(a)
+        pad = np.zeros((nmax,) + a.shape[1:], a.dtype)
+        pad[:n_local] = a
+        t = torch.from_numpy(pad).to(dev)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        if rank == dst:
+            out[key] = np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)])
+    return out if rank == dst else None

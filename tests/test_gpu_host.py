@@ -127,3 +127,35 @@ def test_dualnet_handle_inference_matches_oracle():
     assert isinstance(pol, torch.Tensor) and np.abs(pol.numpy() - rp).max() <= 1e-4 and np.abs(val.numpy() - rv).max() <= 1e-4
     lg, _ = net.inference_with_policy_logits(torch.from_numpy(x))
     assert np.abs(lg.numpy() - ref.evaluator()(x, True)[0]).max() <= 1e-4
+
+
+def test_c1_one_game_puct100_through_the_dropin_loop():
+    """BASELINE.json configs[0] plumbing: one 9x9 game played move by move through GoBoard + MCTSTree.search_best_move
+    (100-visit PUCT, batch 1) exactly like the reference's worker / GTP loop, against the oracle's game with the same
+    evaluator and noise keys."""
+    from oracle import oracle as orc
+    from tamago_b200.board.go_board import GoBoard
+    from tamago_b200.board.stone import Stone
+    from tamago_b200.mcts.tree import MCTSTree
+    from tamago_b200.mcts.time_manager import TimeManager, TimeControl
+    zob = orc.default_zobrist(9)
+    ot = orc.OracleTree(9, orc.hashnet, tree_size=4096)
+    want = ot.selfplay_game(7.0, zob, seed=31, game=1, visits=100, never_resign=False, use_puct=True)
+    board = GoBoard(9, 7.0, True)
+    board.zobrist_table = zob
+    tree = MCTSTree(_HashNet(), batch_size=1, seed=31)
+    tm = TimeManager(TimeControl.CONSTANT_PLAYOUT, constant_visits=100)
+    color, moves, passes = Stone.BLACK, [], 0
+    for _ in range(2 * 81):
+        tree._game_counter = 0                                   # noise key: game id 1 for every move of this game
+        pos = tree.search_best_move(board, color, tm, {})
+        if pos == -1:
+            break
+        board.put_stone(pos, color)
+        moves.append(pos)
+        passes = passes + 1 if pos == 0 else 0
+        color = Stone.get_opponent_color(color)
+        if passes == 2:
+            break
+    assert moves == [int(p) for p in want["pos"]]
+    assert len(moves) > 20

@@ -19,6 +19,14 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mine = shard_for_rank(11)
     moves, secs = reduce_counters(100 * (rank + 1), 1.0 + rank)
+    import numpy as np
+    from tamago_b200.selfplay.shard import gather_training_arrays
+    n = 3 + 2 * rank
+    got = gather_training_arrays({"value": np.full(n, rank, np.int32), "policy": np.full((n, 4), rank + 0.5)})
+    if rank == 0:
+        assert list(got["value"]) == [0, 0, 0, 1, 1, 1, 1, 1] and got["policy"].shape == (8, 4) and got["policy"][5, 0] == 1.5
+    else:
+        assert got is None
     out.put((rank, mine, moves, secs))
     dist.barrier()
     dist.destroy_process_group()
