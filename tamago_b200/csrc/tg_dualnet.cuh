@@ -240,12 +240,14 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
             uint32_t wc = 0;
             for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
                 for (int l = 0; l < L; l++) {
-                    for (int tap = 0; tap < 9; tap++, wc++) {
+                    // the stem's taps are small (4 KB): six of them share a stage, so the stem needs two transfers
+                    const int nxfer = l == 0 ? 2 : 9;
+                    for (int x = 0; x < nxfer; x++, wc++) {
                         const uint32_t st = wc % W_STAGES, par = (wc / W_STAGES) & 1;
                         mbar_wait(bar_wempty + 8 * st, par ^ 1);
-                        const uint32_t bytes = l == 0 ? W_STEM_TAP_BYTES : W_STAGE_BYTES;
-                        const __half* src = l == 0 ? P.w_stem + (size_t)tap * (W_STEM_TAP_BYTES / 2)
-                                                   : P.w_conv + (size_t)(l - 1) * W_LAYER_HALVES + (size_t)tap * (W_STAGE_BYTES / 2);
+                        const uint32_t bytes = l == 0 ? (x == 0 ? 6 : 3) * W_STEM_TAP_BYTES : W_STAGE_BYTES;
+                        const __half* src = l == 0 ? P.w_stem + (size_t)x * 6 * (W_STEM_TAP_BYTES / 2)
+                                                   : P.w_conv + (size_t)(l - 1) * W_LAYER_HALVES + (size_t)x * (W_STAGE_BYTES / 2);
                         mbar_arrive_expect_tx(bar_wfull + 8 * st, bytes);
                         bulk_g2s(smem_u32(smem + NG::OFF_W + st * W_STAGE_BYTES), src, bytes, bar_wfull + 8 * st);
                     }
@@ -270,13 +272,19 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                     // tiles they read (t-1, t), and a tile's accumulators are released right after its last-tap MMAs.
                     // Safe with in-place activations because taps are issued in order: the last tap (+1,+1) of later
                     // tiles only reads rows beyond tile t, and every earlier tap of every tile has completed by then.
-                    for (int tap = 0; tap < 9; tap++, wc++) {
-                        const uint32_t st = wc % W_STAGES, par = (wc / W_STAGES) & 1;
-                        mbar_wait(bar_wfull + 8 * st, par);
-                        tc_fence_after();
+                    uint32_t st = 0;
+                    for (int tap = 0; tap < 9; tap++) {
+                        const bool new_stage = l != 0 || tap == 0 || tap == 6;      // stem: taps 0..5 and 6..8 share a stage
+                        if (new_stage) {
+                            st = wc % W_STAGES;
+                            mbar_wait(bar_wfull + 8 * st, (wc / W_STAGES) & 1);
+                            tc_fence_after();
+                            wc++;
+                        }
+                        const bool stage_done = l != 0 || tap == 5 || tap == 8;
                         const uint32_t row16 = (uint32_t)(NG::L0 + (tap / 3 - 1) * NG::PITCH + (tap % 3 - 1));
                         const uint32_t ah = a_hi0 + row16, al = a_lo0 + row16;
-                        const uint32_t wst = w_addr16 + st * (W_STAGE_BYTES / 16);
+                        const uint32_t wst = w_addr16 + st * (W_STAGE_BYTES / 16) + (l == 0 ? (tap % 6) * (W_STEM_TAP_BYTES / 16) : 0);
                         const uint32_t whs = wst | LBO_HS, whl = (wst + W_HS_BYTES / 16) | LBO_HL;
 #pragma unroll
                         for (int t = 0; t < NG::TILES; t++) {
@@ -300,7 +308,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                                     }
                                 }
                                 if (tap == 8) tc_commit(bar_accfull + 8 * t);             // this tile's accumulators are complete
-                                if (t == NG::TILES - 1) tc_commit(bar_wempty + 8 * st);   // stage is free once these MMAs have read it
+                                if (t == NG::TILES - 1 && stage_done) tc_commit(bar_wempty + 8 * st);   // stage free once these MMAs have read it
                             }
                             __syncwarp();
                         }
@@ -320,28 +328,30 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
         float* vact = reinterpret_cast<float*>(smem + NG::OFF_VACT);
         float* logit_s = reinterpret_cast<float*>(smem + NG::OFF_LOGIT);
         uint32_t lc = 0;
-        for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-            const int slot0 = grp * G;
-            // ---- input planes -> fp16 rows (channels 0..5; 6..15 zero) ----
-            static_assert(NG::TILES * 128 == EPI_THREADS, "one epilogue thread per row");
-            for (int r = et; r < NG::TILES * 128; r += EPI_THREADS) {
-                const int b = r / NG::BR, q = r - b * NG::BR;
-                const int y = q / NG::PITCH - 1, x = q - (y + 1) * NG::PITCH;
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (b < G && y >= 0 && x < N && slot0 + b < n_slots) {
-                    const float* pl = planes + (size_t)(slot0 + b) * 6 * NG::NN + y * N + x;
-                    __half2 h01 = __floats2half2_rn(pl[0], pl[NG::NN]);
-                    __half2 h23 = __floats2half2_rn(pl[2 * NG::NN], pl[3 * NG::NN]);
-                    __half2 h45 = __floats2half2_rn(pl[4 * NG::NN], pl[5 * NG::NN]);
-                    v.x = *reinterpret_cast<uint32_t*>(&h01); v.y = *reinterpret_cast<uint32_t*>(&h23);
-                    v.z = *reinterpret_cast<uint32_t*>(&h45);
-                }
-                *reinterpret_cast<uint4*>(smem + NG::OFF_HI + (NG::L0 + r) * 16) = v;
-                *reinterpret_cast<uint4*>(smem + NG::OFF_HI + NG::PLANE_BYTES + (NG::L0 + r) * 16) = make_uint4(0, 0, 0, 0);
+        // input planes of a group -> fp16 rows (channels 0..5; 6..15 zero); thread et owns row et, a row of tile et / 128
+        static_assert(NG::TILES * 128 == EPI_THREADS, "one epilogue thread per row");
+        auto load_planes = [&](int grp_) {
+            const int r = et, s0 = grp_ * G;
+            const int b = r / NG::BR, q = r - b * NG::BR;
+            const int y = q / NG::PITCH - 1, x = q - (y + 1) * NG::PITCH;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (b < G && y >= 0 && x < N && s0 + b < n_slots) {
+                const float* pl = planes + (size_t)(s0 + b) * 6 * NG::NN + y * N + x;
+                __half2 h01 = __floats2half2_rn(pl[0], pl[NG::NN]);
+                __half2 h23 = __floats2half2_rn(pl[2 * NG::NN], pl[3 * NG::NN]);
+                __half2 h45 = __floats2half2_rn(pl[4 * NG::NN], pl[5 * NG::NN]);
+                v.x = *reinterpret_cast<uint32_t*>(&h01); v.y = *reinterpret_cast<uint32_t*>(&h23);
+                v.z = *reinterpret_cast<uint32_t*>(&h45);
             }
+            *reinterpret_cast<uint4*>(smem + NG::OFF_HI + (NG::L0 + r) * 16) = v;
+            *reinterpret_cast<uint4*>(smem + NG::OFF_HI + NG::PLANE_BYTES + (NG::L0 + r) * 16) = make_uint4(0, 0, 0, 0);
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar_actready + 8 * tile0);               // thread et wrote row et, a row of tile et / 128
+            mbar_arrive(bar_actready + 8 * tile0);
+        };
+        if ((int)blockIdx.x < ngroups) load_planes(blockIdx.x);
+        for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+            const int slot0 = grp * G;
 
             for (int l = 0; l < L; l++, lc++) {
                 const bool is_conv1 = (l >= 1) && ((l - 1) % 2 == 0);
@@ -349,6 +359,13 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                 const bool last = (l == L - 1);
                 const float inv_scale = 1.0f / P.scale[l];
                 float hp0 = 0.f, hp1 = 0.f, hv = 0.f;
+                // conv2: the first quarter of the skip row is fetched (L2) before the accumulators are waited for
+                float4 sk0[4];
+                if (is_conv2 && tile0 < NG::TILES) {
+                    const float* sr = P.skip + (size_t)blockIdx.x * SKIP_FLOATS_PER_CTA + (size_t)(tile0 * 128 + quarter * 32 + lane) * 4;
+#pragma unroll
+                    for (int qd = 0; qd < 4; qd++) sk0[qd] = *reinterpret_cast<const float4*>(sr + (size_t)qd * 2048);
+                }
                 // one lane per warp polls its tile's MMA-completion barrier
                 if (lane == 0) mbar_wait(bar_accfull + 8 * tile0, lc & 1);
                 __syncwarp();
@@ -368,7 +385,8 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                         float4 sk[4];
                         if (is_conv2) {                                                 // issue the skip loads early (L2)
 #pragma unroll
-                            for (int qd = 0; qd < 4; qd++) sk[qd] = *reinterpret_cast<const float4*>(skip_row + (size_t)(c0 / 4 + qd) * 2048);
+                            for (int qd = 0; qd < 4; qd++)
+                                sk[qd] = c0 == 0 ? sk0[qd] : *reinterpret_cast<const float4*>(skip_row + (size_t)(c0 / 4 + qd) * 2048);
                         }
                         const uint32_t lane_col = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * 128 + c0;
                         TG_TMEM_LD16(lane_col, v);                                      // main accumulator: x_hi . w_hi
@@ -432,20 +450,38 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                 }
                 if (P.dbg && blockIdx.x == 0 && lc < 14 && et == 0) P.dbg[lc * 4 + 3] = clock64();
             }
+            // the last layer wrote nothing to shared memory and its accumulators have been read: the next group's planes
+            // can go in now, so that its stem MMAs overlap the heads below
+            if (grp + (int)gridDim.x < ngroups) load_planes(grp + gridDim.x);
             // ---- heads: FC layers + softmax (policy_head.py:37-40, value_head.py:38-40, dual_net.py:81-106) ----
-            tc_fence_before();
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            for (int o = et; o < NG::A; o += EPI_THREADS) {
-                float acc[G];
+            {   // policy FC: (output, quarter of the input) work items over all epilogue threads; partial sums are staged in
+                // the x_lo buffer (idle until the next stem epilogue rewrites it) and added in a fixed order
+                constexpr int JP = 4, JN = (2 * NG::NN + JP - 1) / JP;
+                static_assert(JP * G * NG::A * 4 <= NG::TILES * 128 * 16, "partial sums do not fit the scratch rows");
+                float* part = reinterpret_cast<float*>(smem + NG::OFF_LO + NG::L0 * 16);
+                for (int wi = et; wi < NG::A * JP; wi += EPI_THREADS) {
+                    const int o = wi % NG::A, jp = wi / NG::A;
+                    const int j0 = jp * JN, j1 = min(2 * NG::NN, j0 + JN);
+                    float acc[G];
 #pragma unroll
-                for (int b = 0; b < G; b++) acc[b] = P.pfc_b[o];
-                for (int j = 0; j < 2 * NG::NN; j++) {
-                    const float w = __ldg(P.pfc_t + (size_t)j * NG::A + o);
+                    for (int b = 0; b < G; b++) acc[b] = 0.0f;
+                    for (int j = j0; j < j1; j++) {
+                        const float w = __ldg(P.pfc_t + (size_t)j * NG::A + o);
 #pragma unroll
-                    for (int b = 0; b < G; b++) acc[b] = fmaf(w, pact[b * 2 * NG::NN + j], acc[b]);
+                        for (int b = 0; b < G; b++) acc[b] = fmaf(w, pact[b * 2 * NG::NN + j], acc[b]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < G; b++) part[(jp * G + b) * NG::A + o] = acc[b];
                 }
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                for (int wi = et; wi < NG::A * G; wi += EPI_THREADS) {
+                    const int o = wi % NG::A, b = wi / NG::A;
+                    float sum = P.pfc_b[o];
 #pragma unroll
-                for (int b = 0; b < G; b++) logit_s[b * NG::A + o] = acc[b];
+                    for (int jp = 0; jp < JP; jp++) sum += part[(jp * G + b) * NG::A + o];
+                    logit_s[b * NG::A + o] = sum;
+                }
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
             {
