@@ -330,7 +330,7 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
         for (int c = 0; c < 2; c++)
             fold(1 + 2 * b + c, w->block_conv_w + ((size_t)b * 2 + c) * 64 * 64 * 9, 64, w->block_bn + ((size_t)b * 2 + c) * 4 * 64, w->block_bn_eps);
 
-    const size_t stem_tap = (size_t)W_STEM_TAP_BYTES / 2, conv_tap = (size_t)W_STAGE_BYTES / 2, hs_halves = (size_t)W_HS_BYTES / 2;
+    const size_t stem_tap = (size_t)W_STEM_TAP_BYTES / 2, conv_tap = (size_t)W_TAP_BYTES / 2;
     std::vector<__half> w_stem(9 * stem_tap), w_conv((size_t)(L - 1) * W_LAYER_HALVES);
     std::vector<float> w32_stem((size_t)6 * 9 * 64), w32_conv((size_t)(L - 1) * 64 * 9 * 64);
     for (int l = 0; l < L; l++) {
@@ -349,23 +349,22 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
                     const double v = ic < cin ? wf[l][((size_t)oc * cin + ic) * 9 + tap] : 0.0;
                     const double vs = v * s;
                     const __half hi = __float2half_rn((float)vs);
-                    const __half lo = __float2half_rn((float)(vs - (double)__half2float(hi)));
-                    const __half his = __float2half_rn(__half2float(hi) / LO_SCALE);          // pairs with x_lo * 2^11
+                    // w_lo is stored * 2^11 like x_lo: the small accumulator then holds 2^11 (x_hi w_lo + x_lo w_hi)
+                    const __half lo = __float2half_rn((float)((vs - (double)__half2float(hi)) * (double)LO_SCALE));
                     // [chunk][row][8]: the stacked tile has 128 rows per chunk (w_hi rows 0..63, w_lo rows 64..127)
                     const size_t hl_hi = ((size_t)(ic / 8) * 128 + oc) * 8 + (ic % 8), hl_lo = hl_hi + 64 * 8;
                     if (l == 0) {
                         lw[(size_t)tap * stem_tap + hl_hi] = hi;
                         lw[(size_t)tap * stem_tap + hl_lo] = lo;
                     } else {
-                        lw[(size_t)tap * conv_tap + ((size_t)(ic / 8) * 64 + oc) * 8 + (ic % 8)] = his;
-                        lw[(size_t)tap * conv_tap + hs_halves + hl_hi] = hi;
-                        lw[(size_t)tap * conv_tap + hs_halves + hl_lo] = lo;
+                        lw[(size_t)tap * conv_tap + hl_hi] = hi;
+                        lw[(size_t)tap * conv_tap + hl_lo] = lo;
                     }
                     if (ic < cin) d32[((size_t)ic * 9 + tap) * 64 + oc] = (float)v;
                 }
     }
     // heads
-    std::vector<float> head_w(3 * 64), head_b(3), pfc_t((size_t)2 * NN * A), pfc_b(A), vfc_w((size_t)3 * NN), vfc_b(3);
+    std::vector<float> head_w(3 * 64), head_b(3), pfc_t((size_t)2 * NN * ((A + 3) & ~3), 0.0f), pfc_b(A), vfc_w((size_t)3 * NN), vfc_b(3);
     for (int k = 0; k < 3; k++) {
         const float* cw = k < 2 ? w->policy_conv_w + (size_t)k * 64 : w->value_conv_w;
         const float* bn = k < 2 ? w->policy_bn : w->value_bn;
@@ -376,7 +375,7 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
     }
     for (int o = 0; o < A; o++) {
         pfc_b[o] = w->policy_fc_b[o];
-        for (int j = 0; j < 2 * NN; j++) pfc_t[(size_t)j * A + o] = w->policy_fc_w[(size_t)o * 2 * NN + j];
+        for (int j = 0; j < 2 * NN; j++) pfc_t[(size_t)j * ((A + 3) & ~3) + o] = w->policy_fc_w[(size_t)o * 2 * NN + j];
     }
     for (int i = 0; i < 3 * NN; i++) vfc_w[i] = w->value_fc_w[i];
     for (int i = 0; i < 3; i++) vfc_b[i] = w->value_fc_b[i];
@@ -737,7 +736,7 @@ extern "C" int tg_bench_kernel(tg_engine* e, const char* name, int32_t slots, in
         CK(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
         cudaFree(d);
         for (int l = 0; l < 14; l++)
-            fprintf(stderr, "layer %2d: mma_issue %7lld  mma_start->epi_start %7lld  epilogue %7lld  epi_end->next_mma_start %7lld\n", l,
+            fprintf(stderr, "layer %2d: mma_issue %7lld  mma_start->epi0_start %7lld  epi0_start->epi3_end %7lld  epi3_end->next_mma_start %7lld\n", l,
                     h[l * 4 + 1] - h[l * 4 + 0], h[l * 4 + 2] - h[l * 4 + 0], h[l * 4 + 3] - h[l * 4 + 2],
                     l < 13 ? h[(l + 1) * 4 + 0] - h[l * 4 + 3] : 0LL);
         *ms_out = 0.f;
