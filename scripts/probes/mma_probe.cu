@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(640, 1) k_probe(int pattern, int reps, long lo
                         }
                     }
                     break;
+                case 17: for (int i = 0; i < 32; i++, n++) mma(tm, a0 + shift + (i & 3) * KS, w0 + (i & 3) * 256, DH, idesc_n(32), 1); break;
+                case 18: for (int i = 0; i < 32; i++, n++) mma(tm, a0 + shift + (i & 3) * KS, w0 + (i & 3) * 256, DH, idesc_n(16), 1); break;
                 case 12:
                     for (int tp = 0; tp < 2; tp++)
                         for (int ks = 0; ks < 4; ks++, n += 4) {
@@ -228,6 +230,69 @@ __global__ void __launch_bounds__(128, 1) k_dual(int issuers, int reps, int over
     }
 }
 
+// ---- CTA pair (cta_group::2): M = 256 (128 rows per CTA), each CTA supplies half of the N rows of B ----
+__device__ __forceinline__ void mma2(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 :: "r"(d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc) : "memory");
+}
+constexpr uint32_t idesc2_n(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((256u >> 4) << 24); }
+__device__ __forceinline__ void cluster_sync()
+{ asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_pair(int issuers, int reps, long long* out)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar[4];
+    __shared__ uint32_t tmem_slot;
+    uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    for (int i = threadIdx.x; i < 200 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3c003c00u, 0x3c00bc00u, 0x38003c00u, 0xbc003c00u);
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; i++) mbar_init(smem_u32(&bar[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = tmem_slot;
+    const int w = threadIdx.x >> 5;
+    const long long t0 = clock64();
+    if (rank == 0 && (threadIdx.x & 31) == 0 && w < issuers) {
+        const uint32_t a0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | ((uint32_t)(PLANE >> 4) << 16);
+        const uint32_t al0 = ((smem_u32(smem + 8 * PLANE) >> 4) & 0x3FFFu) | ((uint32_t)(PLANE >> 4) << 16);
+        const uint32_t w1 = ((smem_u32(smem + 16 * PLANE) >> 4) & 0x3FFFu) | ((1024u >> 4) << 16);          // 64 rows per CTA, chunks 1 KB apart
+        const uint32_t w2 = ((smem_u32(smem + 16 * PLANE + 8192) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);    // 32 rows per CTA, chunks 512 B apart
+        constexpr uint32_t DH = (128u >> 4) | (1u << 14);
+        constexpr uint32_t KS = 2 * PLANE / 16;
+        const int tiles_per = 4 / issuers;
+        long long n = 0;
+        for (int r = 0; r < reps; r++) {
+            const uint32_t shift = 16 + (r % 9);
+            for (int tt = 0; tt < tiles_per; tt++) {
+                const int t = w * tiles_per + tt;
+                for (int ks = 0; ks < 4; ks++, n += 2) {
+                    mma2(tm + t * 128, a0 + shift + t * 128 + ks * KS, w1 + ks * 128, DH, idesc2_n(128), 1);
+                    mma2(tm + t * 128 + 64, al0 + shift + t * 128 + ks * KS, w2 + ks * 64, DH, idesc2_n(64), 1);
+                }
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar[w])) : "memory");
+        mbar_wait(smem_u32(&bar[w]), 0);
+        out[4 + w] = clock64() - t0;
+        out[8 + w] = n;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync();
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(512));
+    }
+}
+
 int main()
 {
     long long* d; long long h[3];
@@ -236,8 +301,21 @@ int main()
     const char* names[] = {"chain N128", "N128 rr4", "chain N64", "N64 rr4", "product order (tile: 4x(N128,N64))", "interleaved (ks: 4xN128, 4xN64)",
                            "chain N256", "N256 rr2", "product order, N64 into separate columns", "N128 rr4 + commit/wait every 8", "chain N192",
                            "per tile 4xN128 then 4xN64", "pairs over 2 tiles interleaved",
-        "product + commit every 16", "product + fence::after every 16", "product + passing try_wait every 16", "product + commit, wait, fence every 16"};
+        "product + commit every 16", "product + fence::after every 16", "product + passing try_wait every 16", "product + commit, wait, fence every 16", "chain N32", "chain N16"};
     cudaFuncSetAttribute(k_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int grid = 2; grid <= 148; grid *= 74)
+    for (int issuers = 1; issuers <= 4; issuers *= 2) {
+        long long hh[16];
+        cudaMemset(d, 0, 16384);
+        k_pair<<<grid, 128, 200 * 1024>>>(issuers, 256, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("pair %d: %s\n", issuers, cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(hh, d, sizeof hh, cudaMemcpyDeviceToHost);
+        long long tot = 0, tmax = 0;
+        for (int w = 0; w < issuers; w++) { tot += hh[8 + w]; tmax = hh[4 + w] > tmax ? hh[4 + w] : tmax; }
+        printf("CTA pair (cta_group::2, M=256), grid %d: %d issuer thread(s): %.1f cyc per (N128, N64) instruction pair\n", grid, issuers, 2.0 * tmax / tot);
+    }
     for (int issuers = 1; issuers <= 4; issuers *= 2)
         for (int ov = 0; ov <= 2; ov++) {
             long long hh[16];
@@ -249,6 +327,23 @@ int main()
             for (int w = 0; w < issuers; w++) { tot += hh[8 + w]; tmax = hh[4 + w] > tmax ? hh[4 + w] : tmax; }
             printf("dual: %d issuer thread(s), overhead %s: %.1f cyc/MMA\n", issuers, ov == 0 ? "none" : ov == 1 ? "per 16 MMAs" : "per 8 MMAs", (double)tmax / tot);
         }
+    // sustained (power-capped) executed throughput: ~1.5 s of back-to-back launches, single CTAs with two issuers vs CTA pairs
+    for (int mode = 0; mode < 2; mode++) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        const int reps = 65536, launches = 12;
+        if (mode == 0) k_dual<<<148, 128, 200 * 1024>>>(2, 1024, 0, d); else k_pair<<<148, 128, 200 * 1024>>>(2, 1024, d);
+        cudaEventRecord(e0);
+        for (int i = 0; i < launches; i++) {
+            if (mode == 0) k_dual<<<148, 128, 200 * 1024>>>(2, reps, 0, d); else k_pair<<<148, 128, 200 * 1024>>>(2, reps, d);
+        }
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("sustained %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        // per CTA and rep: 4 tiles x 4 k-steps x (N128 + N64) on 128 rows
+        const double flop = (double)launches * 148 * reps * 16.0 * 2.0 * 128 * 16 * 192;
+        printf("sustained %s: %.1f ms, %.1f TFLOP/s executed\n", mode == 0 ? "single CTAs, 2 issuers" : "CTA pairs, 2 issuers on the leader", ms, flop / ms / 1e9);
+    }
     const char* inames[] = {"tight flag poll", "TMEM loads", "shared stores", "integer math", "sleeping poll", "L2 loads", "no extra warps"};
     for (int fill = 0; fill < 2; fill++)
     for (int interf = 0; interf <= 6; interf++) {
@@ -274,7 +369,7 @@ int main()
         printf("grid %3d data %s: %.1f cyc/MMA, kernel %.2f ms (3 reps) -> %.0f MHz effective, %.1f TFLOP/s executed\n", grid, fill ? "random" : "zero",
                (double)h[1] / h[2], ms, 3.0 * h[1] / ms / 1e3, flop / ms / 1e9);
     }
-    for (int p = 0; p <= 16; p++) {
+    for (int p = 0; p <= 18; p++) {
         k_probe<<<1, 128, 200 * 1024>>>(p, 64, d, 6, 1);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("pattern %d: %s\n", p, cudaGetErrorString(e)); return 1; }
