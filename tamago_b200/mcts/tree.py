@@ -8,6 +8,9 @@
 get_komi(); it is not modified.  The whole search -- expansion, feature planes, DualNet, selection, backup -- runs on
 the device for the single game of this tree; batches of games go through tamago_b200.selfplay instead.
 """
+import json
+import select
+import sys
 import time
 
 import numpy as np
@@ -83,42 +86,111 @@ class MCTSTree:
         self.to_move = color
         return self._finish(e, e.genmove(mode=MODE_SH, visits=visits, play=False))
 
-    def search_best_move(self, board, color, time_manager, analysis_query=None):
-        visits = time_manager.get_num_visits_threshold(color)
-        strict = bool(getattr(time_manager, "is_strict", lambda: getattr(time_manager.mode, "name", "") == "STRICT_PLAYOUT")())
+    def _run_puct(self, board, color, visits, strict):
         e = self._setup_position(board, color, visits, False)
         self.to_move = color
+        self._board_size = board.get_board_size()
+        return self._finish(e, e.genmove(mode=MODE_PUCT, visits=visits, strict=strict, play=False))
+
+    @staticmethod
+    def _is_strict(time_manager):
+        return bool(getattr(time_manager, "is_strict", lambda: getattr(time_manager.mode, "name", "") == "STRICT_PLAYOUT")())
+
+    def _write_analysis(self, board, analysis_query):
+        mode = analysis_query.get("mode", "lz")
+        sys.stdout.write(self.get_root().get_analysis(board, mode, self.get_pv_lists))
+        sys.stdout.flush()
+
+    def search_best_move(self, board, color, time_manager, analysis_query=None):
+        """mcts/tree.py:57-105.  A non-empty analysis_query makes the search report like MCTSTree.search does (tree.py:155-174);
+        the whole visit budget runs on the device in one call, so the report is written once, from the final tree."""
+        visits = time_manager.get_num_visits_threshold(color)
         start = time.time()
-        pos = self._finish(e, e.genmove(mode=MODE_PUCT, visits=visits, strict=strict, play=False))
+        pos = self._run_puct(board, color, visits, self._is_strict(time_manager))
         root = self.get_root()
+        if analysis_query and root.get_num_children() > 1:
+            self._write_analysis(board, analysis_query)
         if hasattr(time_manager, "set_search_speed"):
             time_manager.set_search_speed(int(root.node_visits), time.time() - start)
         return pos
 
+    def search(self, board, color, time_manager, analysis_query):
+        """mcts/tree.py:130-174: run the PUCT budget of time_manager from `board` and, when analysis_query is not empty,
+        write the lz / cgos analysis of the root to stdout."""
+        self._run_puct(board, color, time_manager.get_num_visits_threshold(color), self._is_strict(time_manager))
+        if analysis_query:
+            self._write_analysis(board, analysis_query)
+
+    def ponder(self, board, color, analysis_query):
+        """mcts/tree.py:108-127: search until input arrives on stdin.  The device search runs fixed budgets, so pondering
+        re-searches with a doubling budget (every round restarts the tree) and reports after each round."""
+        from .time_manager import TimeManager, TimeControl
+        visits, cap = 256, int(analysis_query.get("max_visits", 65536))
+        while True:
+            tm = TimeManager(TimeControl.STRICT_PLAYOUT, constant_visits=visits)
+            self._run_puct(board, color, visits, True)
+            if analysis_query:
+                self._write_analysis(board, analysis_query)
+            if visits >= cap:
+                break
+            if analysis_query.get("ponder", False):
+                try:
+                    rlist, _, _ = select.select([sys.stdin], [], [], 0)
+                except (ValueError, OSError):
+                    rlist = [True]
+                if rlist:
+                    break
+            visits = min(cap, visits * 2)
+
+    def search_with_callback(self, board, color, callback):
+        """mcts/tree.py:177-196 (used by animation/ only): single-descent stepping is not exposed by the device engine."""
+        raise NotImplementedError("search_with_callback: per-descent stepping is host-driven in the reference (animation.py); "
+                                  "the device search runs whole budgets")
+
     def get_root(self):
         e, res = self._last
         k = int(res["num_children"][0])
-        return MCTSNodeView(e.node(0, 0), improved=res["improved"][0, :k].copy())
+        return MCTSNodeView(e.node(0, 0), improved=res["improved"][0, :k].copy(), max_actions=e.A)
+
+    def _node_at(self, index):
+        e, _ = self._last
+        return MCTSNodeView(e.node(0, index), max_actions=e.A)
 
     @property
     def node(self):
-        e, _ = self._last
-        return [MCTSNodeView(e.node(0, i)) for i in range(self.num_nodes)]
+        return [self._node_at(i) for i in range(self.num_nodes)]
+
+    def to_dict(self):
+        """mcts/tree.py:489-506."""
+        return {"node": [nd.to_dict() for nd in self.node], "num_nodes": int(self.num_nodes), "root": 0,
+                "current_root": int(self.current_root), "batch_size": int(self.batch_size), "cgos_mode": bool(self.cgos_mode),
+                "to_move": "black" if color_value(self.to_move) == 1 else "white"}
+
+    def dump_to_json(self, board, superko):
+        """mcts/tree.py:476-486 + mcts/dump.py:10-33 (tamago-dump_tree)."""
+        from ..program import PROGRAM_NAME, VERSION, PROTOCOL_VERSION
+        state = {"dump_version": 2, "tree": self.to_dict(), "board_size": board.get_board_size(), "komi": board.get_komi(),
+                 "move_history": [("black" if color_value(c) == 1 else "white", int(p)) for (c, p, *_r) in board.get_move_history()],
+                 "handicap_history": [int(p) for p in board.get_handicap_history()], "superko": superko,
+                 "name": PROGRAM_NAME, "version": VERSION, "protocol_version": PROTOCOL_VERSION}
+        return json.dumps(state)
 
     def get_pv_lists(self, root, coord):
-        """mcts/tree.py:432-473: principal variation below every root child that has been expanded."""
-        e, _ = self._last
+        """mcts/tree.py:432-449: principal variation below every visited root child."""
         pv = {}
         for i in range(root.get_num_children()):
-            if root.children_visits[i] == 0:
-                continue
-            seq, idx = [coord.convert_to_gtp_format(root.get_child_move(i))], root.get_child_index(i)
-            while idx >= 0:
-                nd = MCTSNodeView(e.node(0, idx))
-                if nd.num_children == 0 or nd.children_visits.max() == 0:
-                    break
-                b = nd.get_best_move_index()
-                seq.append(coord.convert_to_gtp_format(nd.get_child_move(b)))
-                idx = nd.get_child_index(b)
-            pv[coord.convert_to_gtp_format(root.get_child_move(i))] = seq
+            if root.children_visits[i] > 0:
+                seq = self.get_best_move_sequence([root.get_child_move(i)], root.get_child_index(i))
+                pv[coord.convert_to_gtp_format(root.get_child_move(i))] = [coord.convert_to_gtp_format(p) for p in seq]
         return pv
+
+    def get_best_move_sequence(self, pv_list, index):
+        """mcts/tree.py:451-473: follow the most visited child (first index on ties) until an unvisited or unexpanded node."""
+        while index >= 0:                      # the reference indexes node[-1] for NOT_EXPANDED: an unused node, visits 0
+            nd = self._node_at(index)
+            if nd.node_visits == 0:
+                break
+            b = nd.get_best_move_index()
+            pv_list.append(nd.get_child_move(b))
+            index = nd.get_child_index(b)
+        return pv_list

@@ -10,6 +10,7 @@ parity tests need from it is recorded here and committed as small .npz files:
                    evaluator and counter-based noise injected on both sides (T3)
   selfplay_9.npz   full self-play games incl. the SGF text (T4)
   dualnet_<N>.npz  DualNet outputs for seeded numpy weights on real planes (T2)
+  analysis_9.npz   lz-analyze / cgos-analyze strings, PV lists and tree dumps of PUCT searches
   eye_table.npz    the 65 536-entry eye LUT of board/pattern.py
 
 Usage:  python tests/golden/make_golden.py --size 9   (and --size 19)
@@ -291,6 +292,50 @@ def gen_search(size, seed, out, sh_visits, puct_visits):
     print(f"search golden: {len(cases)} cases -> {out}")
 
 
+def gen_analysis(size, seed, out):
+    """GTP analysis surface: lz-analyze / cgos-analyze strings (mcts/node.py:399-482), PV lists
+    (mcts/tree.py:432-473) and tamago-dump_tree JSON (mcts/dump.py:10) of PUCT searches with injected net/noise."""
+    import contextlib
+    import io
+    import json
+    from board.go_board import GoBoard
+    from board.stone import Stone
+    from mcts.tree import MCTSTree
+    from mcts.time_manager import TimeManager, TimeControl
+    net = HashNet()
+    patch = NoisePatch(seed=seed)
+    movelists = positions_for_search(size, seed + 1, 5)
+    ml_flat, ml_off = [], [0]
+    for ml in movelists:
+        ml_flat += ml; ml_off.append(len(ml_flat))
+    meta, lz_stdout, lz, cgos, pv, dump = [], [], [], [], [], []
+    for pi, ml in enumerate(movelists):
+        b = GoBoard(board_size=size, komi=7.0, check_superko=True)
+        color = Stone.BLACK
+        for p in ml:
+            b.put_stone(p, color); color = Stone.get_opponent_color(color)
+        for visits, batch in ((60, 1), (90, 8)):
+            tree = MCTSTree(net, tree_size=4096, batch_size=batch)
+            patch.key(pi, b.moves)
+            tm = TimeManager(TimeControl.CONSTANT_PLAYOUT, constant_visits=visits)
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+                mv = tree.search_best_move(b, color, tm, {"mode": "lz", "interval": 0})
+            root = tree.get_root()
+            meta.append([pi, visits, batch, mv, color.value, tree.num_nodes])
+            lz_stdout.append(buf.getvalue())
+            lz.append(root.get_analysis(b, "lz", tree.get_pv_lists))
+            cgos.append(root.get_analysis(b, "cgos", tree.get_pv_lists))
+            pv.append(json.dumps(tree.get_pv_lists(root, b.coordinate)))
+            dump.append(tree.dump_to_json(b, True))
+    from board.zobrist_hash import hash_bit_mask
+    np.savez_compressed(out, size=size, seed=seed, zobrist=np.asarray(hash_bit_mask, np.uint64),
+                        movelist=np.array(ml_flat, np.int16), movelist_off=np.array(ml_off, np.int64),
+                        meta=np.array(meta, np.int64), lz_stdout=np.array(lz_stdout), lz=np.array(lz), cgos=np.array(cgos),
+                        pv=np.array(pv), dump=np.array(dump))
+    print(f"analysis golden: {len(meta)} cases -> {out}")
+
+
 def gen_selfplay(size, seed, out, visits, n_games):
     """selfplay/worker.py loop with injected net/noise; keeps the SGF text."""
     import tempfile
@@ -444,6 +489,8 @@ def main():
             gen_search(N, 77, os.path.join(HERE, f"search_{N}.npz"), [16, 50, 400], [(100, 1), (120, 8)])
         else:
             gen_search(N, 77, os.path.join(HERE, f"search_{N}.npz"), [50], [(40, 1)])
+    if want("analysis") and N == 9:
+        gen_analysis(N, 91, os.path.join(HERE, "analysis_9.npz"))
     if want("selfplay") and N == 9:
         gen_selfplay(N, 5, os.path.join(HERE, "selfplay_9.npz"), visits=16, n_games=3)
     if want("rldata") and N == 9:
