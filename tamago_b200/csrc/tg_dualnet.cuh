@@ -187,21 +187,25 @@ constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128
 
 // ------------------------------------------------------------------------------------------------
 // Geometry of the flattened, halo-padded board group held by one CTA.
-//   point (y, x) of board b  ->  row  b*BR + PITCH + y*PITCH + x      (PITCH = N+1: one shared halo column,
-//   one shared halo line between consecutive boards); tap (dy, dx) = row shift dy*PITCH + dx.
+//   point (y, x) of board b  ->  row  b*BR + y*PITCH + x      (PITCH = N+1: column N of every line is the halo column
+//   shared by two lines, line N of every board is the halo line shared by two boards; the halo above the first board
+//   is the L0 leading zero rows); tap (dy, dx) = row shift dy*PITCH + dx.
 // ------------------------------------------------------------------------------------------------
 template <int N, int G> struct NetGeo {
     static constexpr int NN = N * N, A = NN + 1;
     static constexpr int PITCH = N + 1;
     static constexpr int BR = PITCH * PITCH;                    // rows per board
     static constexpr int MROWS = G * BR;
-    static constexpr int TILES = (MROWS + 127) / 128;
+    // rows that have to be COMPUTED end with the last point of the last board: its trailing halo line only has to exist
+    // (as zeros) for the downward taps.  13x13 (two boards) and 19x19: three 128-row tiles instead of four.
+    static constexpr int OUT_ROWS = (G - 1) * BR + (N - 1) * PITCH + N;
+    static constexpr int TILES = (OUT_ROWS + 127) / 128;
     static constexpr int L0 = ((PITCH + 1 + 7) / 8) * 8;         // leading zero rows
     static constexpr int R = ((L0 + TILES * 128 + PITCH + 1 + 7) / 8) * 8;   // rows allocated per chunk plane
     static constexpr int PLANE_BYTES = R * 16;                   // one 8-channel chunk plane
     static constexpr int ACT_BYTES = 8 * PLANE_BYTES;            // one fp16 copy (hi or lo) of the activations
     // TMEM: tile t owns columns [128 t, 128 t + 128): main accumulator (x_hi w_hi) | small accumulator (corrections * 2^11)
-    static_assert(TILES == 4, "the two-half layer schedule and the epilogue warp mapping assume four 128-row tiles");
+    static_assert(TILES == 3 || TILES == 4, "the two-half layer schedule and the epilogue warp mapping assume three or four 128-row tiles");
     static constexpr int AP4 = (A + 3) & ~3;                     // policy FC outputs are produced four at a time
     static constexpr int JP = N >= 19 ? 5 : 3;                   // policy FC: input range split into JP partial sums
     // shared memory carve-up
@@ -262,9 +266,10 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < W_STAGES; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 2); }
-        for (int t = 0; t < 4; t++) { mbar_init(bar_accfull + 8 * t, 2); mbar_init(bar_actready + 8 * t, 128); }
+        // bar_accfull[t]: the owner's commit + the commit of the other tile of the same half, if there is one
+        for (int t = 0; t < 4; t++) { mbar_init(bar_accfull + 8 * t, (t ^ 1) < NG::TILES ? 2 : 1); mbar_init(bar_actready + 8 * t, 128); }
         mbar_init(bar_bnd, 1);
-        mbar_init(bar_headin, EPI_THREADS);
+        mbar_init(bar_headin, NG::TILES * 128);
         mbar_init(bar_headfree, HEAD_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -331,9 +336,22 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int t = 2 * h + tt;
+                    if (t >= NG::TILES) {
+                        // three-tile geometry: the second half has one tile.  Its nine taps drain the weight ring as fast as
+                        // L2 can refill it (16 KB per tap and SM, all SMs in phase), so a second issuer would not add
+                        // throughput (measured: sharing the tile by operand or by taps is no faster); this issuer only keeps
+                        // the ring in step: it takes every stage of the half and hands it straight back.
+                        const int nstage = l == 0 ? (9 + W_STEM_TAPS_PER_STAGE - 1) / W_STEM_TAPS_PER_STAGE : 9;
+                        for (int x = 0; x < nstage; x++, wc++) {
+                            mbar_wait_relaxed(bar_wfull + 8 * (wc % W_STAGES), (wc / W_STAGES) & 1);
+                            if (lane == 0) mbar_arrive(bar_wempty + 8 * (wc % W_STAGES));
+                            __syncwarp();
+                        }
+                        continue;
+                    }
                     // input rows of both tiles of the half (own rows + the neighbour rows the taps reach)
                     mbar_wait(bar_actready + 8 * (2 * h), lc & 1);
-                    mbar_wait(bar_actready + 8 * (2 * h + 1), lc & 1);
+                    if (2 * h + 1 < NG::TILES) mbar_wait(bar_actready + 8 * (2 * h + 1), lc & 1);
                     tc_fence_after();
                     if (P.dbg && blockIdx.x == 0 && lc < 14 && lane == 0 && t == 0) P.dbg[lc * 4 + 0] = clock64();
                     uint32_t st = 0;
@@ -370,7 +388,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                             }
                             if (tap == 8) {                                             // this issuer is done with the half
                                 tc_commit(bar_accfull + 8 * t);
-                                if (tt == 0) tc_commit(bar_accfull + 8 * (t + 1));      // ... and no longer reads the next tile's head
+                                if (tt == 0 && t + 1 < NG::TILES) tc_commit(bar_accfull + 8 * (t + 1));   // ... and no longer reads the next tile's head
                             }
                             if (tap == 3 && tt == 1) tc_commit(bar_accfull + 8 * (t - 1));   // the previous tile's tail has been read
                             if (t == 2 && tap == 3) tc_commit(bar_bnd);               // tile 1's tail rows may be rewritten
@@ -382,7 +400,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                 if (P.dbg && blockIdx.x == 0 && lc < 14 && lane == 0 && tt == 0) P.dbg[lc * 4 + 1] = clock64();
             }
         }
-    } else if (warp < EPI_WARPS) {
+    } else if (warp < NG::TILES * 4) {
         // ===== epilogue warps: thread et owns row et (tile et / 128, TMEM lane et % 128) =====
         const int et = threadIdx.x;                              // 0..EPI_THREADS-1
         const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
@@ -392,11 +410,11 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
         float* pact = reinterpret_cast<float*>(smem + NG::OFF_PACT);
         float* vact = reinterpret_cast<float*>(smem + NG::OFF_VACT);
         uint32_t lc = 0, gi = 0;
-        static_assert(NG::TILES * 128 == EPI_THREADS, "one epilogue thread per row");
+        static_assert(NG::TILES * 128 <= EPI_THREADS, "one epilogue thread per computed row");
         const int r = et;
         const int b = r / NG::BR, q = r - b * NG::BR;
-        const int y = q / NG::PITCH - 1, x = q - (y + 1) * NG::PITCH;
-        const bool interior = (b < G) && (y >= 0) && (x < N);
+        const int y = q / NG::PITCH, x = q - y * NG::PITCH;
+        const bool interior = (b < G) && (y < N) && (x < N);
         const float cap = interior ? 60000.0f : 0.0f;                        // halo rows stay zero; fp16 range guard
         float* skip_row = P.skip + (size_t)blockIdx.x * SKIP_FLOATS_PER_CTA + (size_t)r * 4;   // [quad][row][4]
         // input planes of a group -> fp16 rows (channels 0..5; 6..15 zero)
@@ -515,10 +533,10 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                     // group's planes go in now, so that its stem MMAs overlap the rest of this layer and the heads
                     if (grp + (int)gridDim.x < ngroups) load_planes(grp + gridDim.x);
                 }
-                if (P.dbg && blockIdx.x == 0 && lc < 14 && et == EPI_THREADS - 128) P.dbg[lc * 4 + 3] = clock64();
+                if (P.dbg && blockIdx.x == 0 && lc < 14 && et == (NG::TILES - 1) * 128) P.dbg[lc * 4 + 3] = clock64();
             }
         }
-    } else {
+    } else if (warp >= WARP_HEAD0 && warp < WARP_HEAD0 + HEAD_WARPS) {
         // ===== head warps: FC layers + softmax (policy_head.py:37-40, value_head.py:38-40, dual_net.py:81-106) =====
         const int ht = threadIdx.x - WARP_HEAD0 * 32, hw = warp - WARP_HEAD0;
         const float* pact = reinterpret_cast<const float*>(smem + NG::OFF_PACT);
