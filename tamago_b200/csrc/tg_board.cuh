@@ -213,7 +213,40 @@ __device__ inline void wb_put_stone(WBoard<N>& b, BScal& s, int pos, int color, 
     }
     if (color == BLACK) s.pris0 += prisoner; else s.pris1 += prisoner;   // :168-171
     __syncwarp();
-    wb_recount(b, lane);
+    if (ncap == 0 && nown <= 1) {
+        // Nothing was captured and at most one own string is extended: liberties and sizes change only around pos,
+        // so the full recount sweep is replaced by a local update with the same result.  Every distinct adjacent
+        // enemy string loses the liberty pos; the stone's string loses pos, gains the empty neighbours of pos that
+        // were not its liberties yet (string.py:411-441 add_stone / 371-409 make_string) and grows by one.
+        if (lane == 0) {
+            int el[4], ne = 0;
+            unsigned gained = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int cc = b.color[q[i]];
+                if (cc == other) {
+                    const int l = b.chain[q[i]];
+                    bool dup = false;
+                    for (int k = 0; k < ne; k++) dup |= (el[k] == l);
+                    if (!dup) { el[ne++] = l; b.ls[l] -= 1u << 16; }
+                } else if (cc == EMPTY) {
+                    bool already = false;
+                    if (nown == 1) {
+                        const int r[4] = { q[i] - G::W, q[i] - 1, q[i] + 1, q[i] + G::W };
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            already |= (r[j] != pos && b.color[r[j]] == color && b.chain[r[j]] == label);
+                    }
+                    if (!already) gained++;
+                }
+            }
+            if (nown == 1) b.ls[label] += (gained << 16) - (1u << 16) + 1u;
+            else b.ls[label] = (gained << 16) | 1u;
+        }
+        __syncwarp();
+    } else {
+        wb_recount(b, lane);
+    }
     if (nown == 0 && prisoner == 1 && (b.ls[label] >> 16) == 1u) {       // :173-177
         s.ko_move = s.moves;
 #pragma unroll

@@ -234,6 +234,11 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
         if (cudaMemcpyAsync(eye, tab.data(), 65536, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "eye table upload"));
         if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "sync"));
         D.zob = z; D.eye = eye;
+        D.prof = nullptr;
+        if (getenv("TG_PROF")) {
+            void* q = nullptr;
+            if (cudaMalloc(&q, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(q, 0, 64 * sizeof(long long)); D.prof = reinterpret_cast<long long*>(q); }
+        }
     }
     if (cfg->evaluator == TG_EVAL_DUALNET_FP32) {
         e->simt_chunk = std::min(e->slot_cap, 8192);
@@ -591,6 +596,13 @@ extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t st
     if (out && out->improved) CK(cudaMemcpyAsync(e->h_improved, D.out_improved, (size_t)games * e->AP * 8, cudaMemcpyDeviceToHost, e->stream));
     if (out && out->visits) CK(cudaMemcpyAsync(e->h_visits, D.out_visits, (size_t)games * e->AP * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    if (D.prof) {
+        long long h[16];
+        CK(cudaMemcpy(h, D.prof, sizeof h, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(D.prof, 0, 64 * sizeof(long long)));
+        fprintf(stderr, "descend profile (game 0, cycles): copy %lld  select %lld (%lld)  put_stone %lld  expand %lld (%lld)  push_leaf %lld (%lld)\n",
+                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7]);
+    }
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
     e->last_eval_ms = 0.f;
     for (int i = 2; i + 1 < ev; i += 2) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->events[i], e->events[i + 1])); e->last_eval_ms += ms; }
@@ -659,6 +671,13 @@ extern "C" int tg_forward(tg_engine* e, const float* planes, int32_t n, int32_t 
     }
     CK(cudaEventRecord(e->events[1], e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    if (D.prof) {
+        long long h[16];
+        CK(cudaMemcpy(h, D.prof, sizeof h, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(D.prof, 0, 64 * sizeof(long long)));
+        fprintf(stderr, "descend profile (game 0, cycles): copy %lld  select %lld (%lld)  put_stone %lld  expand %lld (%lld)  push_leaf %lld (%lld)\n",
+                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7]);
+    }
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
     return TG_OK;
 }

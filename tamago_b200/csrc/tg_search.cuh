@@ -54,6 +54,7 @@ struct Dev {
     int* out_visits;         // [games][AP]
     // constants
     const u64* zob; const uint8_t* eye;
+    long long* prof;         // optional clock64 accumulators of game 0 (development: TG_PROF=1)
 };
 
 template <int N> struct WarpSmem {
@@ -335,18 +336,23 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
             const int cutoff = strict ? 0 : top1 - top2;
             if (remaining < cutoff) { if (lane == 0) gs[GS_DONE] = 1; __syncwarp(); break; }
         }
+        const bool prof = D.prof && g == 0 && lane == 0;
+        long long pt0 = prof ? clock64() : 0;
         wb_copy<N>(sm.scratch, sm.root, lane);                                   // tree.py:147
+        if (prof) { const long long c = clock64(); D.prof[0] += c - pt0; pt0 = c; }
         BScal s = rs;
         int color = root_color, cur = 0, plen = 0;
         unsigned* path = D.path + ((size_t)g * D.cap + gs[GS_NLEAF]) * D.max_depth;
         bool fail = false;
         for (;;) {
             const int next = select_puct<G::AP>(t, cur, D.cgos != 0, lane);      // :213
+            if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
             const size_t row = (size_t)cur * G::AP;
             const int mv = t.action[row + next];
             if (lane == 0) path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
             plen++;
             wb_put_stone<N>(sm.scratch, s, mv, color, D.zob, hh, hp, lane);      // :217
+            if (prof) { const long long c = clock64(); D.prof[2] += c - pt0; pt0 = c; }
             color = opp(color);
             if (lane == 0) { t.hdr[(size_t)cur * H_STRIDE + H_VL] += 1; t.cvl[row + next] += 1; }      // :221
             __syncwarp();
@@ -358,12 +364,16 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
             if (t.cvis[row + next] + t.cvl[row + next] < expand_threshold + 1) { // :231-241
                 int ci = t.cidx[row + next];
                 if (ci == NOT_EXPANDED) {
+                    if (prof) pt0 = clock64();
                     ci = expand_node<N>(D, t, g, gs, sm.scratch, sm.an, s, color, hh, move_key, lane);
+                    if (prof) { const long long c = clock64(); D.prof[3] += c - pt0; pt0 = c; D.prof[6]++; }
                     if (ci < 0) { fail = true; break; }
                     if (lane == 0) t.cidx[row + next] = ci;
                     __syncwarp();
                 }
+                if (prof) pt0 = clock64();
                 push_leaf<N>(D, g, gs, sm.scratch, s, color, path, plen, ci, lane, -1, true);
+                if (prof) { const long long c = clock64(); D.prof[4] += c - pt0; pt0 = c; D.prof[7]++; }
                 break;
             }
             cur = t.cidx[row + next];

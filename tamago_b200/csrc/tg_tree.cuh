@@ -57,13 +57,29 @@ __device__ inline int select_puct(const Tree& t, int node, bool cgos, int lane)
     const double sq = sqrt((double)(h[H_NV] + h[H_VL] + 1));
     const size_t row = (size_t)node * AP;
     double bv = 0.0; int bi = 0x7fffffff;
-    for (int i = lane; i < k; i += 32) {
-        const int cv = t.cvis[row + i] + t.cvl[row + i];
-        const double q = cv != 0 ? ddiv((double)t.cvsum[row + i], (double)cv) : 0.0;
-        const double u = ddiv(dmul(dmul(1.0, t.cpol[row + i]), sq), (double)(cv + 1));
-        double v = dadd(q, u);
-        if (cgos && i == k - 1) v = dsub(v, 0.1);
-        if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
+    // the child rows live in the HBM/L2 node pool: fetch four 32-child sweeps at a time so that one memory latency covers
+    // four sweeps of the float64 arithmetic (the selection order, lowest index first per lane, is unchanged).  Measured
+    // alternatives that were not faster: issuing the eight divisions of a chunk back to back (register spills), ranking
+    // with reciprocal-multiply scores and dividing exactly only for the near-maximal children.
+    constexpr int CH = 4;
+    for (int i0 = lane; i0 < k; i0 += 32 * CH) {
+        int cv[CH]; float vs[CH]; double pol[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const int i = i0 + 32 * c;
+            cv[c] = 0; vs[c] = 0.0f; pol[c] = 0.0;
+            if (i < k) { cv[c] = t.cvis[row + i] + t.cvl[row + i]; vs[c] = t.cvsum[row + i]; pol[c] = t.cpol[row + i]; }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const int i = i0 + 32 * c;
+            if (i >= k) break;
+            const double q = cv[c] != 0 ? ddiv((double)vs[c], (double)cv[c]) : 0.0;
+            const double u = ddiv(dmul(dmul(1.0, pol[c]), sq), (double)(cv[c] + 1));
+            double v = dadd(q, u);
+            if (cgos && i == k - 1) v = dsub(v, 0.1);
+            if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
+        }
     }
     warp_argmax_d(bv, bi);
     return bi;
