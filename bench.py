@@ -249,6 +249,43 @@ def run_ours(a):
                  "kernel_tflops": d_evals * FLOP_PER_EVAL[n] / (d_ev_ms * 1e-3) / 1e12 if d_ev_ms > 0 else None,
                  "note": "same workload and results; leaves of one phase reached by the same path are evaluated once (engine dedup=1)"}
 
+    # third measurement: the 19x19 half of the metric (BASELINE.json configs[3] geometry: 1024 games/GPU, 400 visits), as an extra
+    extra19 = None
+    if a.also_19 and n != 19:
+        eng.close()
+        g19 = 1024
+        eng = tb.Engine(board_size=19, games=g19, max_visits=visits, komi=7.0, superko=True, device=local,
+                        evaluator=tb.EVAL_DUALNET_TC, dedup=False, seed=4321 + rank)
+        eng.load_state_dict(random_init_state_dict(19, 0))
+        eng.reset(game_ids=np.arange(g19, dtype=np.uint64) + np.uint64(rank * 10_000_000), never_resign=np.ones(g19, np.uint8))
+        for _ in range(2):
+            eng.genmove(mode=tb.MODE_SH, visits=visits, play=True, full=True)
+        barrier()
+        x_ms = x_ev_ms = 0.0
+        x_moves = x_evals = 0
+        t2 = time.perf_counter()
+        for _ in range(min(a.steps, 4)):
+            r = eng.genmove(mode=tb.MODE_SH, visits=visits, play=True, full=True)
+            if int((r["error"] != 0).sum()):
+                raise SystemExit("bench.py: 19x19 games reported search errors")
+            x_moves += int((r["move"] >= 0).sum()); x_ms += eng.last_device_ms
+            x_ev_ms += eng.bench_kernel("eval_ms"); x_evals += int(r["evals"][1])
+        barrier()
+        x_wall = time.perf_counter() - t2
+        xs = torch.tensor([x_ms, x_wall, float(x_moves)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            xmx = xs.clone(); dist.all_reduce(xmx, op=dist.ReduceOp.MAX)
+            xsm = xs.clone(); dist.all_reduce(xsm, op=dist.ReduceOp.SUM)
+            x_ms_max, x_wall_max, x_moves_all = xmx[0].item(), xmx[1].item(), xsm[2].item()
+        else:
+            x_ms_max, x_wall_max, x_moves_all = x_ms, x_wall, float(x_moves)
+        x_tf = x_evals * FLOP_PER_EVAL[19] / (x_ev_ms * 1e-3) / 1e12 if x_ev_ms > 0 else 0.0
+        extra19 = {"workload": f"19x19, {g19} parallel games/GPU, {visits}-visit Gumbel sequential halving, super-ko on",
+                   "value": x_moves_all / (x_ms_max * 1e-3), "unit": "moves/s", "e2e": x_moves_all / x_wall_max,
+                   "ms_per_step": x_ms_max / min(a.steps, 4), "evals_per_step": x_evals / min(a.steps, 4),
+                   "kernel_tflops": x_tf, "roofline_frac": x_tf / measured_peaks()["bf16_tflops_sustained"],
+                   "flop_per_eval": FLOP_PER_EVAL[19]}
+
     stats = torch.tensor([dev_ms, wall, float(moves), eval_ms, float(evals), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -284,6 +321,8 @@ def run_ours(a):
     }
     if extra is not None:
         line["result_preserving_dedup"] = extra
+    if extra19 is not None:
+        line["board_19x19"] = extra19
     if a.cpu_baseline and world == 1:
         v, w, m = cpu_port_run(n, visits, 1, a.cpu_moves)
         line["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": 1, "kind": "port",
@@ -304,6 +343,7 @@ def main():
     ap.add_argument("--visits", type=int, default=400)
     ap.add_argument("--dedup", type=int, default=0)
     ap.add_argument("--also-dedup", type=int, default=1, help="also report the result-preserving dedup mode as an extra object")
+    ap.add_argument("--also-19", type=int, default=1, help="also report the 19x19 half of the metric (1024 games/GPU) as an extra object")
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--cpu-moves", type=int, default=16, help="moves of the bounded cpu_baseline sample")
     ap.add_argument("--ref-moves", type=int, default=6, help="moves per process and step in the --impl reference arm")

@@ -42,7 +42,7 @@ def launches():
         ms = v / 1e6 if d["Metric Unit"].startswith("n") else (v / 1e3 if d["Metric Unit"].startswith("u") else v)
         a = agg.setdefault(short(d["Kernel Name"]), [0, 0.0]); a[0] += 1; a[1] += ms; total += ms
     with open(os.path.join(OUT, f"{tag}_launches.md"), "w") as f:
-        f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 3 --cpu-baseline 0`\n\n")
+        f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 3 --cpu-baseline 0 --also-19 0 --also-dedup 0`\n\n")
         f.write("Per-launch times are cold-cache and serialised; compare SHARES with bench.py's `roofline.kernel_share_of_step`.\n\n")
         f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, (n, ms) in sorted(agg.items(), key=lambda x: -x[1][1]):

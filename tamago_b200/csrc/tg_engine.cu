@@ -237,7 +237,7 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
         D.prof = nullptr;
         if (getenv("TG_PROF")) {
             void* q = nullptr;
-            if (cudaMalloc(&q, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(q, 0, 64 * sizeof(long long)); D.prof = reinterpret_cast<long long*>(q); }
+            if (cudaMalloc(&q, 64 * sizeof(long long)) == cudaSuccess) { cudaMemset(q, 0, 64 * sizeof(long long)); e->allocs.push_back(q); D.prof = reinterpret_cast<long long*>(q); }
         }
     }
     if (cfg->evaluator == TG_EVAL_DUALNET_FP32) {
