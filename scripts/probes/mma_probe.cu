@@ -293,6 +293,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_pair(int i
     }
 }
 
+// two issuers sharing ONE tile: issuer w takes every other "tap" (8 MMAs: 4 x (N128, N64)) into its own accumulator pair,
+// with the kernel's per-tap bookkeeping (commit + wait + fence) after each tap
+__global__ void __launch_bounds__(128, 1) k_coop(int issuers, int reps, long long* out)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar[4], bar2, bar3;
+    __shared__ uint32_t tmem_slot;
+    for (int i = threadIdx.x; i < 200 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3c003c00u, 0x3c00bc00u, 0x38003c00u, 0xbc003c00u);
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; i++) mbar_init(smem_u32(&bar[i]), 1); mbar_init(smem_u32(&bar2), 1 << 20); mbar_init(smem_u32(&bar3), 1);
+                            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = tmem_slot;
+    const int w = threadIdx.x >> 5;
+    const long long t0 = clock64();
+    if ((threadIdx.x & 31) == 0 && w < issuers) {
+        const uint32_t a0 = ((smem_u32(smem) >> 4) & 0x3FFFu) | ((uint32_t)(PLANE >> 4) << 16);
+        const uint32_t al0 = ((smem_u32(smem + 8 * PLANE) >> 4) & 0x3FFFu) | ((uint32_t)(PLANE >> 4) << 16);
+        const uint32_t w0 = ((smem_u32(smem + 16 * PLANE) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+        constexpr uint32_t DH = (128u >> 4) | (1u << 14);
+        constexpr uint32_t KS = 2 * PLANE / 16;
+        long long n = 0;
+        for (int r = 0; r < reps; r++) {
+            if ((r % issuers) != w) continue;
+            const uint32_t shift = 16 + (r % 9);
+            for (int ks = 0; ks < 4; ks++, n += 2) {
+                mma(tm + w * 128, a0 + shift + ks * KS, w0 + ks * 256, DH, idesc_n(128), 1);
+                mma(tm + w * 128 + 64, al0 + shift + ks * KS, w0 + ks * 256, DH, idesc_n(64), 1);
+            }
+            tc_commit(smem_u32(&bar2)); mbar_wait(smem_u32(&bar3), 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        tc_commit(smem_u32(&bar[w]));
+        mbar_wait(smem_u32(&bar[w]), 0);
+        out[4 + w] = clock64() - t0;
+        out[8 + w] = n;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(512));
+    }
+}
+
 int main()
 {
     long long* d; long long h[3];
@@ -303,6 +353,18 @@ int main()
                            "per tile 4xN128 then 4xN64", "pairs over 2 tiles interleaved",
         "product + commit every 16", "product + fence::after every 16", "product + passing try_wait every 16", "product + commit, wait, fence every 16", "chain N32", "chain N16"};
     cudaFuncSetAttribute(k_dual, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int issuers = 1; issuers <= 4; issuers *= 2) {
+        long long hh[16];
+        cudaMemset(d, 0, 16384);
+        k_coop<<<1, 128, 200 * 1024>>>(issuers, 1024, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("coop %d: %s\n", issuers, cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(hh, d, sizeof hh, cudaMemcpyDeviceToHost);
+        long long tot = 0, tmax = 0;
+        for (int w = 0; w < issuers; w++) { tot += hh[8 + w]; tmax = hh[4 + w] > tmax ? hh[4 + w] : tmax; }
+        printf("one tile shared by %d issuer(s), taps alternate, bookkeeping per tap: %.1f cyc per (N128, N64) pair\n", issuers, 2.0 * tmax / tot);
+    }
     cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int grid = 2; grid <= 148; grid *= 74)
     for (int issuers = 1; issuers <= 4; issuers *= 2) {
