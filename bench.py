@@ -312,8 +312,8 @@ def run_ours(a):
         "gpu_launches": launches_all,
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "k_dualnet_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": 2401.0 * evals / max(1, a.steps * 5),
-                     "traffic_source": "profiles/r01_dualnet_tc.md: 236.1 MB DRAM read+write for a 98.3 k-evaluation launch = 2401 B per evaluation (algorithmic 2284 B: planes in, policy/value out), scaled to this run's mean evaluations per launch (5 launches per step)",
+                     "frac": achieved / peak, "traffic": 2455.0 * evals / max(1, a.steps * 5),
+                     "traffic_source": "profiles/r01_dualnet_tc.md: 241.3 MB DRAM read+write for a 98.3 k-evaluation launch = 2455 B per evaluation (algorithmic 2284 B: planes in, policy/value out), scaled to this run's mean evaluations per launch (5 launches per step)",
                      "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                      "evals_per_step": evals / a.steps, "flop_per_eval": flop, "kernel_ms_per_step": eval_ms / a.steps,
                      "kernel_share_of_step": eval_ms / dev_ms if dev_ms else None,
