@@ -110,7 +110,7 @@ def cpu_port_run(size, visits, procs, moves_per_proc, seed=0):
 
 
 # ----------------------------------------------------------------------------------------------------------
-def run_reference(a):
+def run_reference(a, out=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -137,7 +137,7 @@ def run_reference(a):
                          "sample": f"{cores} processes x {mpp} moves from the empty board per step, oracle C search + torch fp32 DualNet (1 thread each)"},
         "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def workload_config(a):
@@ -149,7 +149,7 @@ def workload_config(a):
             "l2": "working set per step (leaf planes + node pool, > 1 GB) exceeds the 126 MB L2; no flush needed"}
 
 
-def run_ours(a):
+def run_ours(a, out=sys.stdout):
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -327,7 +327,7 @@ def run_ours(a):
         v, w, m = cpu_port_run(n, visits, 1, a.cpu_moves)
         line["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": 1, "kind": "port",
                                 "sample": f"{m} moves of one {n}x{n} game from the empty board at {visits} visits, oracle C search + torch fp32 DualNet, 1 thread ({w:.1f} s)"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -348,10 +348,18 @@ def main():
     ap.add_argument("--cpu-moves", type=int, default=16, help="moves of the bounded cpu_baseline sample")
     ap.add_argument("--ref-moves", type=int, default=6, help="moves per process and step in the --impl reference arm")
     a = ap.parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    # stdout carries exactly one JSON line: anything libraries write to fd 1 meanwhile (e.g. the NCCL version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved_stdout, "w")
+    try:
+        if a.impl == "reference":
+            run_reference(a, real_stdout)
+        else:
+            run_ours(a, real_stdout)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
