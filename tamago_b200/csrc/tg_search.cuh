@@ -60,8 +60,8 @@ struct Dev {
 template <int N> struct WarpSmem {
     WBoard<N> root;
     WBoard<N> scratch;
-    WAnalysis<N> an;
-    double s0[Geo<N>::AP];
+    alignas(16) WAnalysis<N> an;     // expansion scratch; PUCT selection stages the child rows here (never live at the same time)
+    alignas(16) double s0[Geo<N>::AP];
     double s1[Geo<N>::AP];
     int16_t memo[Geo<N>::AP];        // sequential halving: root child -> first leaf of this phase that went through it
 };
@@ -345,7 +345,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
         unsigned* path = D.path + ((size_t)g * D.cap + gs[GS_NLEAF]) * D.max_depth;
         bool fail = false;
         for (;;) {
-            const int next = select_puct<G::AP>(t, cur, D.cgos != 0, lane);      // :213
+            static_assert(sizeof(WAnalysis<N>) >= 3 * G::AP * 4, "child-row staging aliases the analysis scratch");
+            const SelStage stage = { sm.s0, reinterpret_cast<int*>(&sm.an), reinterpret_cast<int*>(&sm.an) + G::AP,
+                                     reinterpret_cast<float*>(&sm.an) + 2 * G::AP };
+            const int next = select_puct<G::AP>(t, cur, D.cgos != 0, lane, stage);      // :213
             if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
             const size_t row = (size_t)cur * G::AP;
             const int mv = t.action[row + next];
