@@ -78,9 +78,12 @@ __device__ inline int select_puct(const Tree& t, int node, bool cgos, int lane, 
     double bv = 0.0; int bi = 0x7fffffff;
     for (int i = lane; i < k; i += 32) {          // (unrolling for overlapping divisions was measured slower: 7.4 k -> 10.6 k cycles)
         const int cv = st.vis[i] + st.vl[i];
-        const double q = cv != 0 ? ddiv((double)st.vsum[i], (double)cv) : 0.0;
-        const double u = ddiv(dmul(dmul(1.0, st.pol[i]), sq), (double)(cv + 1));
-        double v = dadd(q, u);
+        // an unvisited child (n + vl = 0) divides by one and has q = 0: x / 1.0 = x and 0.0 + x = x exactly, so the two
+        // correctly rounded divisions are only executed by lanes whose child has been visited (most sweeps of a deep,
+        // wide node skip them altogether)
+        const double num = dmul(dmul(1.0, st.pol[i]), sq);
+        double v = num;
+        if (cv != 0) v = dadd(ddiv((double)st.vsum[i], (double)cv), ddiv(num, (double)(cv + 1)));
         if (cgos && i == k - 1) v = dsub(v, 0.1);
         if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
     }
