@@ -671,13 +671,6 @@ extern "C" int tg_forward(tg_engine* e, const float* planes, int32_t n, int32_t 
     }
     CK(cudaEventRecord(e->events[1], e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    if (D.prof) {
-        long long h[16];
-        CK(cudaMemcpy(h, D.prof, sizeof h, cudaMemcpyDeviceToHost));
-        CK(cudaMemset(D.prof, 0, 64 * sizeof(long long)));
-        fprintf(stderr, "descend profile (game 0, cycles): copy %lld  select %lld (%lld)  put_stone %lld  expand %lld (%lld)  push_leaf %lld (%lld)\n",
-                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7]);
-    }
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
     return TG_OK;
 }

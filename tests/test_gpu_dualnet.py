@@ -109,3 +109,35 @@ def test_13x13_tensor_core_kernel_matches_fp64():
     logits, val = e.forward(x, use_logit=True)
     e.close()
     assert np.abs(logits - ref_logits).max() <= TOL and np.abs(val - ref_val).max() <= TOL
+
+
+@pytest.mark.parametrize("size", [9, 13, 19])
+def test_tensor_core_kernel_is_batch_invariant(golden_dir, size):
+    """A board's policy / value must not depend on its slot, its group, its tile or the batch size: the same planes are
+    evaluated in batches of 1, G-1, G, G+1, one full wave + 1 and in reversed order, and every result must be
+    BIT-identical (the kernel has no cross-board reduction and a fixed summation order)."""
+    import tamago_b200 as tb
+    g = np.load(os.path.join(golden_dir, f"dualnet_{9 if size == 13 else size}.npz"))
+    rs = np.random.RandomState(11)
+    G = {9: 5, 13: 2, 19: 1}[size]
+    n = 148 * G + 1
+    if size == 13:
+        x = np.zeros((n, 6, 13, 13), np.float32)
+        stones = rs.randint(0, 3, (n, 13, 13))
+        for c in range(3):
+            x[:, c] = (stones == c)
+        x[:, 5] = np.where(rs.rand(n) < 0.5, 1.0, -1.0)[:, None, None]
+    else:
+        x = g["planes"][rs.randint(0, len(g["planes"]), n)].copy()
+    e = tb.Engine(board_size=size, games=64, max_visits=64, evaluator=tb.EVAL_DUALNET_TC)
+    e.load_state_dict(_weights(size, 99))
+    full_p, full_v = e.forward(x, use_logit=True)
+    rev_p, rev_v = e.forward(x[::-1].copy(), use_logit=True)
+    assert np.array_equal(rev_p[::-1], full_p) and np.array_equal(rev_v[::-1], full_v)
+    for m in sorted({1, max(1, G - 1), G, G + 1, 2 * G + 1}):
+        p, v = e.forward(x[:m], use_logit=True)
+        assert np.array_equal(p, full_p[:m]) and np.array_equal(v, full_v[:m]), m
+        p, v = e.forward(x[n - m:], use_logit=False)              # softmax output path, boards in other slots
+        sp, sv = e.forward(x, use_logit=False)
+        assert np.array_equal(p, sp[n - m:]) and np.array_equal(v, sv[n - m:]), m
+    e.close()
