@@ -136,6 +136,16 @@ int  tg_planes(tg_engine* e, float* out);
 /* DualNet.inference / inference_with_policy_logits (dual_net.py:81-106): planes [n][6][N][N] -> policy [n][N*N+1], value [n][3] */
 int  tg_forward(tg_engine* e, const float* planes, int32_t n, int32_t use_logit, float* policy, float* value);
 
+/* Device-resident evaluation (zero copy): the evaluator batch lives in device buffers owned by the engine -- planes
+ * [slot_cap][6][N][N], policy [slot_cap][N*N+1], value [slot_cap][3], all fp32 -- which a caller may alias (e.g. as torch
+ * tensors through __cuda_array_interface__ / DLPack).  tg_forward_device runs DualNet.inference / inference_with_policy_logits
+ * (dual_net.py:81-106) on the first n slots, asynchronously on the engine's stream (tg_stream, a cudaStream_t);
+ * tg_sync waits for everything queued on it. */
+int   tg_eval_buffers(tg_engine* e, float** planes, float** policy, float** value, int32_t* slot_cap);
+int   tg_forward_device(tg_engine* e, int32_t n, int32_t use_logit);
+void* tg_stream(tg_engine* e);
+int   tg_sync(tg_engine* e);
+
 /* MCTSTree.generate_move_with_sequential_halving (tree.py:318) / search_best_move (tree.py:57) for every game.
  * play = 1 additionally runs the body of selfplay_worker's move loop (worker.py:58-87). */
 int  tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t strict, int32_t play, tg_step_result* out);

@@ -58,6 +58,10 @@ EXPORTS = {
     "tg_set_to_move": (C.c_int, [C.c_void_p, i32p]),
     "tg_planes": (C.c_int, [C.c_void_p, f32p]),
     "tg_forward": (C.c_int, [C.c_void_p, f32p, C.c_int32, C.c_int32, f32p, f32p]),
+    "tg_eval_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), i32p]),
+    "tg_forward_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "tg_stream": (C.c_void_p, [C.c_void_p]),
+    "tg_sync": (C.c_int, [C.c_void_p]),
     "tg_genmove": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(StepResult)]),
     "tg_tree_size": (C.c_int, [C.c_void_p, C.c_int32, i32p]),
     "tg_read_node": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(NodeView)]),

@@ -652,6 +652,38 @@ extern "C" int tg_planes(tg_engine* e, float* outp)
     return TG_OK;
 }
 
+extern "C" int tg_eval_buffers(tg_engine* e, float** planes, float** policy, float** value, int32_t* slot_cap)
+{
+    if (!e) return fail(TG_ERR_ARG, "null engine");
+    if (planes) *planes = e->D.planes;
+    if (policy) *policy = e->D.policy;
+    if (value) *value = e->D.value;
+    if (slot_cap) *slot_cap = e->slot_cap;
+    return TG_OK;
+}
+
+extern "C" int tg_forward_device(tg_engine* e, int32_t n, int32_t use_logit)
+{
+    if (!e || n < 0 || n > e->slot_cap) return fail(TG_ERR_ARG, "n outside [0, slot_cap]");
+    CK(cudaSetDevice(e->cfg.device));
+    // the slot count is read by the kernel from device memory: stage it through the engine's pinned block
+    e->h_gs[0] = n;
+    CK(cudaMemcpyAsync(e->D.n_slots, e->h_gs, 4, cudaMemcpyHostToDevice, e->stream));
+    int rc = 0;
+    DISPATCH_N(e, rc = launch_net<BN>(e, use_logit, n));
+    return rc;
+}
+
+extern "C" void* tg_stream(tg_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+extern "C" int tg_sync(tg_engine* e)
+{
+    if (!e) return fail(TG_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    return TG_OK;
+}
+
 extern "C" int tg_forward(tg_engine* e, const float* planes, int32_t n, int32_t use_logit, float* policy, float* value)
 {
     if (!e || !planes || !policy || !value || n < 0) return fail(TG_ERR_ARG, "bad argument");

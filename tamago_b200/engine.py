@@ -121,6 +121,32 @@ class Engine:
         check(self.lib.tg_forward(self.h, _ptr(x, C.c_float), x.shape[0], int(use_logit), _ptr(pol, C.c_float), _ptr(val, C.c_float)))
         return pol, val
 
+    # -- device-resident evaluation (zero copy) ------------------------------------------------------
+    def eval_tensors(self):
+        """torch views of the engine's evaluator batch on the device: planes [slot_cap, 6, N, N], policy [slot_cap, N*N+1],
+        value [slot_cap, 3] (fp32).  They alias engine memory: fill `planes[:n]`, call forward_device(n), read the others."""
+        import torch
+        p, q, v, cap = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int32()
+        check(self.lib.tg_eval_buffers(self.h, C.byref(p), C.byref(q), C.byref(v), C.byref(cap)))
+
+        class _View:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+        dev = torch.device("cuda", torch.cuda.current_device())
+        mk = lambda ptr, shape: torch.as_tensor(_View(ptr.value, shape), device=dev)
+        return (mk(p, (cap.value, 6, self.n, self.n)), mk(q, (cap.value, self.A)), mk(v, (cap.value, 3)))
+
+    def forward_device(self, n, use_logit=True):
+        """DualNet on the first n slots of the device batch, asynchronous on the engine's stream (see sync / stream)."""
+        check(self.lib.tg_forward_device(self.h, int(n), int(use_logit)))
+
+    @property
+    def stream(self):
+        return self.lib.tg_stream(self.h)
+
+    def sync(self):
+        check(self.lib.tg_sync(self.h))
+
     # -- search -----------------------------------------------------------------------------------
     def genmove(self, mode=MODE_SH, visits=400, strict=False, play=False, full=True):
         g, s = self.games, self.stride

@@ -141,3 +141,26 @@ def test_tensor_core_kernel_is_batch_invariant(golden_dir, size):
         sp, sv = e.forward(x, use_logit=False)
         assert np.array_equal(p, sp[n - m:]) and np.array_equal(v, sv[n - m:]), m
     e.close()
+
+
+def test_device_resident_forward_aliases_engine_buffers(golden_dir):
+    """tg_eval_buffers / tg_forward_device / tg_sync: torch tensors alias the engine's device batch (zero copy) and give the
+    same bits as the host-buffer call."""
+    import torch
+    import tamago_b200 as tb
+    g = np.load(os.path.join(golden_dir, "dualnet_9.npz"))
+    x = g["planes"][:37]
+    e = tb.Engine(board_size=9, games=16, max_visits=32, evaluator=tb.EVAL_DUALNET_TC)
+    e.load_state_dict(_weights(9, 5))
+    ref_p, ref_v = e.forward(x, use_logit=True)
+    planes, policy, value = e.eval_tensors()
+    assert planes.is_cuda and planes.shape[1:] == (6, 9, 9) and policy.shape[1] == 82 and value.shape[1] == 3
+    policy.zero_(); value.zero_()
+    planes[:len(x)].copy_(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    e.forward_device(len(x), use_logit=True)
+    e.sync()
+    assert np.array_equal(policy[:len(x)].cpu().numpy(), ref_p) and np.array_equal(value[:len(x)].cpu().numpy(), ref_v)
+    with pytest.raises(Exception):
+        e.forward_device(planes.shape[0] + 1)
+    e.close()
