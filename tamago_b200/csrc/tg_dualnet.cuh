@@ -337,10 +337,11 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                 for (int h = 0; h < 2; h++) {
                     const int t = 2 * h + tt;
                     if (t >= NG::TILES) {
-                        // three-tile geometry: the second half has one tile.  Its nine taps drain the weight ring as fast as
-                        // L2 can refill it (16 KB per tap and SM, all SMs in phase), so a second issuer would not add
-                        // throughput (measured: sharing the tile by operand or by taps is no faster); this issuer only keeps
-                        // the ring in step: it takes every stage of the half and hands it straight back.
+                        // three-tile geometry: the second half has one tile and issuer A takes it alone.  (It runs at ~900
+                        // cycles per tap, bound by A's per-tap bookkeeping next to busy epilogue warps, not by the weight stream;
+                        // sharing the tile between the issuers makes the half faster but then the epilogue of tiles 0 and 1 is
+                        // the critical path -- measured, profiles/r01_mma_probe.md.)  This issuer only keeps the ring in step:
+                        // it takes every stage of the half and hands it straight back.
                         const int nstage = l == 0 ? (9 + W_STEM_TAPS_PER_STAGE - 1) / W_STEM_TAPS_PER_STAGE : 9;
                         for (int x = 0; x < nstage; x++, wc++) {
                             mbar_wait_relaxed(bar_wfull + 8 * (wc % W_STAGES), (wc / W_STAGES) & 1);
