@@ -37,10 +37,8 @@
 namespace tg {
 
 constexpr int NET_F = 64;                 // filters (dual_net.py:25)
-constexpr int W_STAGES = 4;
 constexpr int W_TAP_BYTES = 8 * 128 * 16;           // one tap: [w_hi | w_lo * 2^11] as a 128-row x 64-channel tile (16 KB)
 constexpr int W_STEM_TAP_BYTES = 2 * 128 * 16;      // stem tap: the same tile with 16 input channels (4 KB)
-constexpr int W_STEM_TAPS_PER_STAGE = W_TAP_BYTES / W_STEM_TAP_BYTES;   // four stem taps share a ring stage
 constexpr int W_LAYER_HALVES = 9 * (W_TAP_BYTES / 2);        // fp16 elements per 64->64 layer
 constexpr int SKIP_FLOATS_PER_CTA = 16 * 512 * 4;
 constexpr float LO_SCALE = 2048.0f;                 // x_lo and w_lo are stored scaled by 2^11; the small accumulator is 2^11 x
@@ -207,12 +205,19 @@ template <int N, int G> struct NetGeo {
     // TMEM: tile t owns columns [128 t, 128 t + 128): main accumulator (x_hi w_hi) | small accumulator (corrections * 2^11)
     static_assert(TILES == 3 || TILES == 4, "the two-half layer schedule and the epilogue warp mapping assume three or four 128-row tiles");
     static constexpr int AP4 = (A + 3) & ~3;                     // policy FC outputs are produced four at a time
+    // weight ring.  Four-tile geometry: four stages of one conv tap (16 KB).  Three-tile geometry: its activation rows are
+    // 32 KB smaller, so the ring holds three stages of TWO taps (32 KB): half as many stage hand-overs for the issuer that
+    // runs the single-tile half alone (its per-tap bookkeeping, not the tensor pipe, bounds that half).
+    static constexpr int TPS = TILES == 3 ? 2 : 1;                // conv taps per stage
+    static constexpr int W_STAGES = TILES == 3 ? 3 : 4;
+    static constexpr int STAGE_BYTES = TPS * W_TAP_BYTES;
+    static constexpr int STEM_TPS = STAGE_BYTES / W_STEM_TAP_BYTES;   // stem taps (4 KB each) per stage
     static constexpr int JP = N >= 19 ? 5 : 3;                   // policy FC: input range split into JP partial sums
     // shared memory carve-up
     static constexpr int OFF_HI = 0;
     static constexpr int OFF_LO = OFF_HI + ACT_BYTES;
     static constexpr int OFF_W = OFF_LO + ACT_BYTES;
-    static constexpr int OFF_BIAS = OFF_W + W_STAGES * W_TAP_BYTES;            // [32 layers][64] fp32
+    static constexpr int OFF_BIAS = OFF_W + W_STAGES * STAGE_BYTES;            // [32 layers][64] fp32
     static constexpr int OFF_HEADW = OFF_BIAS + 32 * 64 * 4;                   // [3][64] + [4]
     static constexpr int OFF_PACT = OFF_HEADW + (3 * 64 + 4) * 4;              // [G][2*NN] policy-head activations
     static constexpr int OFF_VACT = OFF_PACT + G * 2 * NN * 4;                 // [G][NN]
@@ -244,15 +249,15 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
     const int L = 1 + 2 * P.blocks;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NG::OFF_BAR);
-    const uint32_t bar_wfull = smem_u32(bars + 0);           // [W_STAGES]
-    const uint32_t bar_wempty = smem_u32(bars + W_STAGES);   // [W_STAGES]
-    const uint32_t bar_accfull = smem_u32(bars + 2 * W_STAGES);          // [4] per tile: accumulators of the layer complete
-    const uint32_t bar_actready = smem_u32(bars + 2 * W_STAGES + 4);     // [4] per tile: next layer's input rows written
-    const uint32_t bar_bnd = smem_u32(bars + 2 * W_STAGES + 8);          // tile 2's upward taps have read the tail of tile 1
-    const uint32_t bar_headin = smem_u32(bars + 2 * W_STAGES + 9);       // head activations of a group are in shared memory
-    const uint32_t bar_headfree = smem_u32(bars + 2 * W_STAGES + 10);    // ... and have been consumed by the head warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * W_STAGES + 11);
-    static_assert((2 * W_STAGES + 11) * 8 + 4 <= 192, "barrier block");
+    const uint32_t bar_wfull = smem_u32(bars + 0);           // [NG::W_STAGES]
+    const uint32_t bar_wempty = smem_u32(bars + NG::W_STAGES);   // [NG::W_STAGES]
+    const uint32_t bar_accfull = smem_u32(bars + 2 * NG::W_STAGES);          // [4] per tile: accumulators of the layer complete
+    const uint32_t bar_actready = smem_u32(bars + 2 * NG::W_STAGES + 4);     // [4] per tile: next layer's input rows written
+    const uint32_t bar_bnd = smem_u32(bars + 2 * NG::W_STAGES + 8);          // tile 2's upward taps have read the tail of tile 1
+    const uint32_t bar_headin = smem_u32(bars + 2 * NG::W_STAGES + 9);       // head activations of a group are in shared memory
+    const uint32_t bar_headfree = smem_u32(bars + 2 * NG::W_STAGES + 10);    // ... and have been consumed by the head warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NG::W_STAGES + 11);
+    static_assert((2 * NG::W_STAGES + 11) * 8 + 4 <= 192, "barrier block");
 
     // ---- one-time setup -------------------------------------------------------------------------
     {   // zero both activation copies once (halo rows stay zero for the lifetime of the CTA)
@@ -265,7 +270,7 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
         if (threadIdx.x < 3) hw[3 * 64 + threadIdx.x] = P.head_b[threadIdx.x];
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < W_STAGES; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 2); }
+        for (int s = 0; s < NG::W_STAGES; s++) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, 2); }
         // bar_accfull[t]: the owner's commit + the commit of the other tile of the same half, if there is one
         for (int t = 0; t < 4; t++) { mbar_init(bar_accfull + 8 * t, (t ^ 1) < NG::TILES ? 2 : 1); mbar_init(bar_actready + 8 * t, 128); }
         mbar_init(bar_bnd, 1);
@@ -289,18 +294,18 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
             uint32_t wc = 0;
             for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
                 for (int l = 0; l < L; l++) {
-                    // the stem's taps are small (4 KB): four of them share a stage, so the stem needs three transfers
-                    const int nxfer = l == 0 ? (9 + W_STEM_TAPS_PER_STAGE - 1) / W_STEM_TAPS_PER_STAGE : 9;
+                    // a stage holds TPS conv taps (16 KB each) or STEM_TPS stem taps (4 KB each)
+                    const int tps = l == 0 ? NG::STEM_TPS : NG::TPS;
+                    const int nxfer = (9 + tps - 1) / tps;
                     for (int h = 0; h < 2; h++) {
                         for (int x = 0; x < nxfer; x++, wc++) {
-                            const uint32_t st = wc % W_STAGES, par = (wc / W_STAGES) & 1;
+                            const uint32_t st = wc % NG::W_STAGES, par = (wc / NG::W_STAGES) & 1;
                             mbar_wait(bar_wempty + 8 * st, par ^ 1);
-                            const uint32_t bytes = l == 0 ? (uint32_t)min(W_STEM_TAPS_PER_STAGE, 9 - x * W_STEM_TAPS_PER_STAGE) * W_STEM_TAP_BYTES
-                                                          : (uint32_t)W_TAP_BYTES;
-                            const __half* src = l == 0 ? P.w_stem + (size_t)x * W_STEM_TAPS_PER_STAGE * (W_STEM_TAP_BYTES / 2)
-                                                       : P.w_conv + (size_t)(l - 1) * W_LAYER_HALVES + (size_t)x * (W_TAP_BYTES / 2);
+                            const uint32_t tap_bytes = l == 0 ? (uint32_t)W_STEM_TAP_BYTES : (uint32_t)W_TAP_BYTES;
+                            const uint32_t bytes = (uint32_t)min(tps, 9 - x * tps) * tap_bytes;
+                            const __half* src = (l == 0 ? P.w_stem : P.w_conv + (size_t)(l - 1) * W_LAYER_HALVES) + (size_t)x * tps * (tap_bytes / 2);
                             mbar_arrive_expect_tx(bar_wfull + 8 * st, bytes);
-                            bulk_g2s(smem_u32(smem + NG::OFF_W + st * W_TAP_BYTES), src, bytes, bar_wfull + 8 * st);
+                            bulk_g2s(smem_u32(smem + NG::OFF_W + st * NG::STAGE_BYTES), src, bytes, bar_wfull + 8 * st);
                         }
                     }
                 }
@@ -342,10 +347,11 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                         // sharing the tile between the issuers makes the half faster but then the epilogue of tiles 0 and 1 is
                         // the critical path -- measured, profiles/r01_mma_probe.md.)  This issuer only keeps the ring in step:
                         // it takes every stage of the half and hands it straight back.
-                        const int nstage = l == 0 ? (9 + W_STEM_TAPS_PER_STAGE - 1) / W_STEM_TAPS_PER_STAGE : 9;
+                        const int tps_idle = l == 0 ? NG::STEM_TPS : NG::TPS;
+                        const int nstage = (9 + tps_idle - 1) / tps_idle;
                         for (int x = 0; x < nstage; x++, wc++) {
-                            mbar_wait_relaxed(bar_wfull + 8 * (wc % W_STAGES), (wc / W_STAGES) & 1);
-                            if (lane == 0) mbar_arrive(bar_wempty + 8 * (wc % W_STAGES));
+                            mbar_wait_relaxed(bar_wfull + 8 * (wc % NG::W_STAGES), (wc / NG::W_STAGES) & 1);
+                            if (lane == 0) mbar_arrive(bar_wempty + 8 * (wc % NG::W_STAGES));
                             __syncwarp();
                         }
                         continue;
@@ -356,19 +362,20 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                     tc_fence_after();
                     if (P.dbg && blockIdx.x == 0 && lc < 14 && lane == 0 && t == 0) P.dbg[lc * 4 + 0] = clock64();
                     uint32_t st = 0;
+                    const int tps = l == 0 ? NG::STEM_TPS : NG::TPS;      // taps per weight stage
                     for (int tap = 0; tap < 9; tap++) {
-                        const bool new_stage = l != 0 || (tap % W_STEM_TAPS_PER_STAGE) == 0;
+                        const bool new_stage = (tap % tps) == 0;
                         if (new_stage) {
-                            st = wc % W_STAGES;
-                            mbar_wait(bar_wfull + 8 * st, (wc / W_STAGES) & 1);
+                            st = wc % NG::W_STAGES;
+                            mbar_wait(bar_wfull + 8 * st, (wc / NG::W_STAGES) & 1);
                             tc_fence_after();
                             wc++;
                         }
-                        const bool stage_done = l != 0 || (tap % W_STEM_TAPS_PER_STAGE) == W_STEM_TAPS_PER_STAGE - 1 || tap == 8;
+                        const bool stage_done = (tap % tps) == tps - 1 || tap == 8;
                         const uint32_t row16 = (uint32_t)(NG::L0 + (tap / 3 - 1) * NG::PITCH + (tap % 3 - 1));
                         const uint32_t ah = a_hi0 + row16, al = a_lo0 + row16;
-                        const uint32_t wst = (w_addr16 + st * (W_TAP_BYTES / 16)
-                                              + (l == 0 ? (tap % W_STEM_TAPS_PER_STAGE) * (W_STEM_TAP_BYTES / 16) : 0)) | LBO_W;
+                        const uint32_t wst = (w_addr16 + st * (NG::STAGE_BYTES / 16)
+                                              + (uint32_t)(tap % tps) * ((l == 0 ? W_STEM_TAP_BYTES : W_TAP_BYTES) / 16)) | LBO_W;
                         if (h == 0 && tt == 1 && tap == 5) {                 // tile 1's downward taps reach into tile 2
                             mbar_wait(bar_actready + 8 * 2, lc & 1);
                             tc_fence_after();
