@@ -205,11 +205,11 @@ template <int N, int G> struct NetGeo {
     // TMEM: tile t owns columns [128 t, 128 t + 128): main accumulator (x_hi w_hi) | small accumulator (corrections * 2^11)
     static_assert(TILES == 3 || TILES == 4, "the two-half layer schedule and the epilogue warp mapping assume three or four 128-row tiles");
     static constexpr int AP4 = (A + 3) & ~3;                     // policy FC outputs are produced four at a time
-    // weight ring.  Four-tile geometry: four stages of one conv tap (16 KB).  Three-tile geometry: its activation rows are
-    // 32 KB smaller, so the ring holds three stages of TWO taps (32 KB): half as many stage hand-overs for the issuer that
-    // runs the single-tile half alone (its per-tap bookkeeping, not the tensor pipe, bounds that half).
-    static constexpr int TPS = TILES == 3 ? 2 : 1;                // conv taps per stage
-    static constexpr int W_STAGES = TILES == 3 ? 3 : 4;
+    // weight ring: a stage holds TWO conv taps (32 KB), which halves the issuers' stage hand-overs (their per-stage
+    // bookkeeping -- wait, fence, commits next to busy epilogue warps -- is what limits the MMA issue rate, measured).
+    // Two stages in the four-tile geometry, three in the three-tile one (its activation rows are 32 KB smaller).
+    static constexpr int TPS = 2;                                 // conv taps per stage
+    static constexpr int W_STAGES = TILES == 3 ? 3 : 2;
     static constexpr int STAGE_BYTES = TPS * W_TAP_BYTES;
     static constexpr int STEM_TPS = STAGE_BYTES / W_STEM_TAP_BYTES;   // stem taps (4 KB each) per stage
     static constexpr int JP = N >= 19 ? 5 : 3;                   // policy FC: input range split into JP partial sums
