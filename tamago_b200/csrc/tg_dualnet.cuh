@@ -19,10 +19,10 @@
 //     64..127 -> small accumulator); only x_lo needs a second, N=64 instruction;
 //   * BatchNorm (eval mode) is folded into the weights/bias on the host; the residual skip goes through a
 //     per-CTA fp32 scratch that stays L2 resident (128 KB per CTA) and is added in conv2's epilogue;
-//   * weights stream from L2 through a 3-stage cp.async.bulk/mbarrier ring (16 KB per tap: [w_hi | w_lo * 2^11];
+//   * weights stream from L2 through a cp.async.bulk/mbarrier ring of two-tap stages (16 KB per tap: [w_hi | w_lo * 2^11];
 //     the x_lo instruction reads the w_hi rows of the same tile, the small accumulator carries a factor 2^11);
-//   * a layer is issued as two halves (tiles 0,1 then tiles 2,3, each over all nine taps, weights streamed once per
-//     half): the epilogue of one half runs under the MMAs of the other, so the tensor pipe never waits for it;
+//   * a layer is issued as two halves (tiles 0,1 then tiles 2,3 -- or tile 2 alone at 13x13 / 19x19, where three tiles
+//     cover the rows -- each over all nine taps, weights streamed once per half): the epilogue of one half runs under the MMAs of the other, so the tensor pipe never waits for it;
 //   * warp roles: 0..15 = epilogue (TMEM -> bias/ReLU/split -> smem; warp w owns rows 32 w .. 32 w + 31),
 //     16 = weight producer, 17 and 20 = MMA issuers (one tile of the half each), 18..19 = heads (FC layers + softmax
 //     of the previous group, overlapped with the next group's convolutions).
