@@ -29,7 +29,8 @@ enum tg_mode { TG_MODE_SH = 0,      /* Gumbel sequential halving: MCTSTree.gener
                TG_MODE_PUCT = 1 };  /* PUCT: MCTSTree.search_best_move, mcts/tree.py:57 */
 enum tg_evaluator { TG_EVAL_DUALNET_TC = 0,   /* tcgen05 tensor-core DualNet (product path) */
                     TG_EVAL_DUALNET_FP32 = 1, /* CUDA-core fp32 DualNet (on-device numerical reference) */
-                    TG_EVAL_HASHNET = 2 };    /* deterministic hash evaluator with exact fp32 outputs (tree parity tests) */
+                    TG_EVAL_HASHNET = 2,      /* deterministic hash evaluator with dyadic fp32 outputs (tree parity tests) */
+                    TG_EVAL_HASHNET2 = 3 };   /* same with non-dyadic outputs (k/1000): fp32 accumulation order is observable */
 
 typedef struct tg_config {
     int32_t board_size;       /* N: 9, 13 or 19 (board/constant.py:4 BOARD_SIZE) */

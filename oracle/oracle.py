@@ -66,6 +66,10 @@ class GameRecord(C.Structure):
     ]
 
 
+class HashNetCtx(C.Structure):
+    _fields_ = [("n", C.c_int), ("variant", C.c_int)]
+
+
 EVAL_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int,
                       C.POINTER(C.c_float), C.POINTER(C.c_float))
 
@@ -121,6 +125,11 @@ def lib():
         "tgo_sizeof_record": (C.c_int, []),
         "tgo_selfplay_game": (C.c_int, [C.c_void_p, C.c_int, C.c_double, u64p, C.c_uint64, C.c_uint64,
                                         C.c_int, C.c_int, C.c_int, C.POINTER(GameRecord), f64p, i16p]),
+        "tgo_hashnet_fn": (C.c_void_p, []),
+        "tgo_ply_digest": (C.c_uint64, [BP]),
+        "tgo_random_game": (C.c_int, [C.c_int, u64p, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_double,
+                                      i16p, u64p]),
+        "tgo_tromp_taylor": (C.c_int, [BP]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -191,6 +200,13 @@ class OracleBoard:
     def count_score(self):
         return lib().tgo_count_score(C.byref(self.b))
 
+    def tromp_taylor(self):
+        """Area score Black - White by flood fill (the adjudication get_final_status.py:15-64 gets from GNU Go)."""
+        return lib().tgo_tromp_taylor(C.byref(self.b))
+
+    def ply_digest(self):
+        return int(lib().tgo_ply_digest(C.byref(self.b)))
+
     def state(self):
         color = np.zeros(self.cells, np.uint8)
         libs = np.zeros(self.cells, np.int16)
@@ -228,6 +244,13 @@ class OracleTree:
         self.n, self.A = n, n * n + 1
         self.evaluator = evaluator
         self.eval_calls = []
+        if evaluator is hashnet or evaluator is hashnet2:
+            # the C twin of the numpy hash evaluators (same bits; tests/test_oracle_search2.py checks it): no Python in the loop
+            self._ctx = HashNetCtx(n, 1 if evaluator is hashnet2 else 0)
+            self._cb = C.cast(lib().tgo_hashnet_fn(), EVAL_FN)
+            self.t = lib().tgo_tree_new(n, tree_size, batch_size, int(cgos_mode), self._cb, C.cast(C.pointer(self._ctx), C.c_void_p))
+            lib().tgo_tree_set_use_libm(self.t, int(use_libm))
+            return
 
         def _cb(_ctx, planes, nb, use_logit, policy, value):
             x = np.ctypeslib.as_array(planes, shape=(nb, 6, n, n))
@@ -298,6 +321,42 @@ class OracleTree:
                     num_children=np.array(rec.num_children[:m]), improved=improved[:m], actions=actions[:m])
 
 
+def random_games(n, zobrist, seed, games, max_plies, p_pass=0.02, p_any_legal=0.3, superko=True, first_game=0):
+    """Bulk differential corpus: `games` random games -> (moves [games, max_plies] int16, counts, digests [games, max_plies]).
+    One digest covers everything observable after a ply (colours, liberties, sizes, ko, prisoners, hash, legality /
+    self-atari / eye / candidate masks of both colours, count_score); numpy twin: ply_digest_np below."""
+    zob = np.ascontiguousarray(zobrist, dtype=np.uint64)
+    moves = np.zeros((games, max_plies), np.int16)
+    dig = np.zeros((games, max_plies), np.uint64)
+    counts = np.zeros(games, np.int32)
+    L = lib()
+    for g in range(games):
+        counts[g] = L.tgo_random_game(n, _p(zob, C.c_uint64), int(superko), seed, first_game + g, max_plies, p_pass, p_any_legal,
+                                      moves[g].ctypes.data_as(C.POINTER(C.c_int16)), dig[g].ctypes.data_as(C.POINTER(C.c_uint64)))
+    return moves, counts, dig
+
+
+def _dw(salt, count):
+    with np.errstate(over="ignore"):
+        return _mix64_np(np.uint64(salt) * np.uint64(0x100000001B3) + np.arange(count, dtype=np.uint64)) | np.uint64(1)
+
+
+def ply_digest_np(d, n):
+    """numpy twin of tgo_ply_digest over a per-ply state dump with the keys of tamago_b200.Engine.play(dump=True):
+    color/libs/size [..., cells], scal [..., 5], hash [...], legal/satari/eye/cand [..., 2, n*n], score [...]."""
+    cells, nn = (n + 2) ** 2, n * n
+    with np.errstate(over="ignore"):
+        acc = d["hash"].astype(np.uint64) * _dw(5, 1)[0]
+        v = d["color"].astype(np.uint64) + np.uint64(4) * d["libs"].astype(np.uint64) + np.uint64(4096) * d["size"].astype(np.uint64)
+        acc = acc + (v * _dw(1, cells)).sum(axis=-1, dtype=np.uint64)
+        m = (d["legal"].astype(np.uint64) + np.uint64(2) * d["eye"].astype(np.uint64) + np.uint64(4) * d["cand"].astype(np.uint64)
+             + np.uint64(8) * d["satari"].astype(np.int64).astype(np.uint64))
+        acc = acc + (m.reshape(m.shape[:-2] + (2 * nn,)) * _dw(2, 2 * nn)).sum(axis=-1, dtype=np.uint64)
+        acc = acc + (d["scal"].astype(np.int64).astype(np.uint64) * _dw(3, 5)).sum(axis=-1, dtype=np.uint64)
+        acc = acc + d["score"].astype(np.int64).astype(np.uint64) * _dw(4, 1)[0]
+    return acc
+
+
 def sh_schedule(m, visits):
     cons = (C.c_int * 64)()
     cnts = (C.c_int * 64)()
@@ -333,6 +392,36 @@ def hashnet(planes, use_logit):
         pol = raw / np.float32(1048576.0)
     v0 = va / np.float32(512.0)
     v1 = vb / np.float32(512.0)
+    v2 = np.float32(1.0) - v0 - v1
+    return pol.astype(np.float32), np.stack([v0, v1, v2], axis=1).astype(np.float32)
+
+
+def hashnet2(planes, use_logit):
+    """hashnet with NON-dyadic fp32 outputs (values k/1000, logits raw/1000 - 4).
+
+    Sums of hashnet's outputs are exact in fp32 and fp64 and in any order; these are not, so trees built with this
+    evaluator pin the reference's fp32, queue-order value accumulation (mcts/tree.py:303-313, mcts/node.py:118-138).
+    """
+    planes = np.asarray(planes, dtype=np.float32)
+    nb = planes.shape[0]
+    flat = planes.reshape(nb, -1)
+    npl = flat.shape[1]
+    nn = npl // 6
+    j = np.arange(npl, dtype=np.uint64)
+    code = (flat + 1.0).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = _mix64_np(np.uint64(3) * j[None, :] + code).sum(axis=1, dtype=np.uint64)
+        idx = np.arange(nn + 1, dtype=np.uint64)
+        r = _mix64_np(h[:, None] + idx[None, :])
+        raw = ((r >> np.uint64(40)) & np.uint64(0xFFFF)).astype(np.float32)
+        va = (_mix64_np(h + np.uint64(1000)) % np.uint64(500)).astype(np.float32)
+        vb = (_mix64_np(h + np.uint64(1001)) % np.uint64(500)).astype(np.float32)
+    if use_logit:
+        pol = raw / np.float32(1000.0) - np.float32(4.0)
+    else:
+        pol = raw / np.float32(1000000.0)
+    v0 = va / np.float32(1000.0)
+    v1 = vb / np.float32(1000.0)
     v2 = np.float32(1.0) - v0 - v1
     return pol.astype(np.float32), np.stack([v0, v1, v2], axis=1).astype(np.float32)
 

@@ -865,3 +865,124 @@ int tgo_selfplay_game(TgoTree *t, int n, double komi, const uint64_t *zob, uint6
     }
     return rec->n_moves;
 }
+
+/* ------------------------------------------------------------------ */
+/* native hash evaluators (ours; numpy twins: oracle.py hashnet / hashnet2) */
+/* ------------------------------------------------------------------ */
+void tgo_hashnet_eval(void *ctx, const float *planes, int nb, int use_logit, float *policy, float *value)
+{
+    const TgoHashNetCtx *c = (const TgoHashNetCtx *)ctx;
+    const int nn = c->n * c->n, npl = 6 * nn, A = nn + 1;
+    for (int s = 0; s < nb; s++) {
+        const float *pl = planes + (size_t)s * npl;
+        uint64_t h = 0;
+        for (int j = 0; j < npl; j++) h += mix64(3ull * (uint64_t)j + (uint64_t)(long long)(pl[j] + 1.0f));
+        for (int i = 0; i < A; i++) {
+            const float raw = (float)((mix64(h + (uint64_t)i) >> 40) & 0xFFFFull);
+            if (c->variant == 0) policy[(size_t)s * A + i] = use_logit ? raw / 8192.0f - 4.0f : raw / 1048576.0f;
+            else policy[(size_t)s * A + i] = use_logit ? raw / 1000.0f - 4.0f : raw / 1000000.0f;
+        }
+        const uint64_t ra = mix64(h + 1000ull), rb = mix64(h + 1001ull);
+        const float va = c->variant == 0 ? (float)(ra & 0xFFull) : (float)(ra % 500ull);
+        const float vb = c->variant == 0 ? (float)(rb & 0xFFull) : (float)(rb % 500ull);
+        const float den = c->variant == 0 ? 512.0f : 1000.0f;
+        const float v0 = va / den, v1 = vb / den;
+        value[s * 3 + 0] = v0; value[s * 3 + 1] = v1; value[s * 3 + 2] = (1.0f - v0) - v1;
+    }
+}
+tgo_eval_fn tgo_hashnet_fn(void) { return tgo_hashnet_eval; }
+
+/* ------------------------------------------------------------------ */
+/* bulk differential corpus (ours): random games with one 64-bit digest */
+/* of the whole observable board state per ply.  The numpy twin of the  */
+/* digest (tests/gpu_util.py ply_digest) is applied to the engine's dump.*/
+/* ------------------------------------------------------------------ */
+static inline uint64_t dw(uint64_t salt, uint64_t i) { return mix64(salt * 0x100000001B3ull + i) | 1ull; }
+
+uint64_t tgo_ply_digest(const TgoBoard *b)
+{
+    const int nn = b->n * b->n;
+    uint64_t acc = b->hash * dw(5, 0);
+    for (int c = 0; c < b->cells; c++) {
+        int col = b->color[c], libs = 0, size = 0;
+        if (col == TGO_BLACK || col == TGO_WHITE) { libs = b->libs[b->chain[c]]; size = b->size[b->chain[c]]; }
+        acc += (uint64_t)(col + 4 * libs + 4096 * size) * dw(1, (uint64_t)c);
+    }
+    uint8_t legal[TGO_MAX_ACTIONS], eye[TGO_MAX_ACTIONS], cand[TGO_MAX_ACTIONS]; int16_t sa[TGO_MAX_ACTIONS];
+    for (int ci = 0; ci < 2; ci++) {
+        tgo_analyze(b, ci == 0 ? TGO_BLACK : TGO_WHITE, legal, sa, eye, cand);
+        for (int i = 0; i < nn; i++)
+            acc += (uint64_t)(legal[i] + 2 * eye[i] + 4 * cand[i] + 8 * (int)sa[i]) * dw(2, (uint64_t)(ci * nn + i));
+    }
+    const int sc[5] = { b->moves, b->ko_pos, b->ko_move, b->prisoner[0], b->prisoner[1] };
+    for (int i = 0; i < 5; i++) acc += (uint64_t)(int64_t)sc[i] * dw(3, (uint64_t)i);
+    acc += (uint64_t)(int64_t)tgo_count_score(b) * dw(4, 0);
+    return acc;
+}
+
+int tgo_random_game(int n, const uint64_t *zob, int superko, uint64_t seed, uint64_t game, int max_plies,
+                    double p_pass, double p_any_legal, int16_t *moves_out, uint64_t *digest_out)
+{
+    TgoBoard b;
+    tgo_board_init(&b, n, 7.0, superko, zob);
+    const int nn = n * n;
+    int color = TGO_BLACK, plies = 0, passes = 0;
+    uint8_t legal[TGO_MAX_ACTIONS], eye[TGO_MAX_ACTIONS], cand[TGO_MAX_ACTIONS]; int16_t sa[TGO_MAX_ACTIONS];
+    for (; plies < max_plies; plies++) {
+        uint64_t r = mix64(mix64(seed + game) + (uint64_t)plies);
+        const double u0 = (double)(r >> 11) * (1.0 / 9007199254740992.0);
+        r = mix64(r);
+        const double u1 = (double)(r >> 11) * (1.0 / 9007199254740992.0);
+        r = mix64(r);
+        tgo_analyze(&b, color, legal, sa, eye, cand);
+        const uint8_t *pool = u1 < p_any_legal ? legal : cand;
+        int cnt = 0;
+        for (int i = 0; i < nn; i++) cnt += pool[i];
+        int pos = TGO_PASS;
+        if (cnt > 0 && u0 >= p_pass) {
+            int pick = (int)(r % (uint64_t)cnt);
+            for (int i = 0; i < nn; i++) if (pool[i] && pick-- == 0) { pos = tgo_onboard_pos(&b, i); break; }
+        }
+        tgo_put_stone(&b, pos, color);
+        moves_out[plies] = (int16_t)pos;
+        digest_out[plies] = tgo_ply_digest(&b);
+        color = opp(color);
+        passes = pos == TGO_PASS ? passes + 1 : 0;
+        if (passes >= 2 && plies > 20) { plies++; break; }
+    }
+    return plies;
+}
+
+/* ------------------------------------------------------------------ */
+/* Tromp-Taylor area score (ours; the adjudication the reference gets   */
+/* from GNU Go, get_final_status.py:15-64, restated as a flood fill):    */
+/* stones + empty regions that reach only one colour.  Black - White.    */
+/* ------------------------------------------------------------------ */
+int tgo_tromp_taylor(const TgoBoard *b)
+{
+    uint8_t seen[TGO_MAX_CELLS];
+    int stack[TGO_MAX_CELLS];
+    memset(seen, 0, sizeof seen);
+    int score = 0;
+    for (int i = 0; i < b->n * b->n; i++) {
+        const int p0 = tgo_onboard_pos(b, i);
+        if (b->color[p0] == TGO_BLACK) { score++; continue; }
+        if (b->color[p0] == TGO_WHITE) { score--; continue; }
+        if (seen[p0]) continue;
+        int sp = 0, cnt = 0, reach = 0;
+        stack[sp++] = p0; seen[p0] = 1;
+        while (sp > 0) {
+            const int p = stack[--sp];
+            cnt++;
+            int q[4]; nbr4(b, p, q);
+            for (int k = 0; k < 4; k++) {
+                const int c = b->color[q[k]];
+                if (c == TGO_BLACK) reach |= 1;
+                else if (c == TGO_WHITE) reach |= 2;
+                else if (c == TGO_EMPTY && !seen[q[k]]) { seen[q[k]] = 1; stack[sp++] = q[k]; }
+            }
+        }
+        if (reach == 1) score += cnt; else if (reach == 2) score -= cnt;
+    }
+    return score;
+}

@@ -154,6 +154,15 @@ int      tgo_selfplay_game(TgoTree *t, int n, double komi, const uint64_t *zob,
                            uint64_t seed, uint64_t game, int visits, int never_resign,
                            int use_puct, TgoGameRecord *rec, double *improved, int16_t *actions);
 
+/* ---- native hash evaluators, bulk corpus digests, Tromp-Taylor (ours) -- */
+typedef struct TgoHashNetCtx { int n, variant; } TgoHashNetCtx;   /* variant 0: oracle.hashnet, 1: oracle.hashnet2 */
+void     tgo_hashnet_eval(void *ctx, const float *planes, int nb, int use_logit, float *policy, float *value);
+tgo_eval_fn tgo_hashnet_fn(void);
+uint64_t tgo_ply_digest(const TgoBoard *b);
+int      tgo_random_game(int n, const uint64_t *zob, int superko, uint64_t seed, uint64_t game, int max_plies,
+                         double p_pass, double p_any_legal, int16_t *moves_out, uint64_t *digest_out);
+int      tgo_tromp_taylor(const TgoBoard *b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -484,8 +484,9 @@ extern "C" int tg_play(tg_engine* e, const int16_t* moves, const uint8_t* colors
 template <int BN> static int launch_net(tg_engine* e, int use_logit, int max_slots)
 {
     const Dev& D = e->D;
-    if (e->cfg.evaluator == TG_EVAL_HASHNET) {
-        k_hashnet<BN><<<(max_slots + 3) / 4, 128, 0, e->stream>>>(D.planes, D.n_slots, use_logit, D.policy, D.value);
+    if (e->cfg.evaluator == TG_EVAL_HASHNET || e->cfg.evaluator == TG_EVAL_HASHNET2) {
+        k_hashnet<BN><<<(max_slots + 3) / 4, 128, 0, e->stream>>>(D.planes, D.n_slots, use_logit, D.policy, D.value,
+                                                                  e->cfg.evaluator == TG_EVAL_HASHNET2 ? 1 : 0);
         e->launches++;
     } else if (e->cfg.evaluator == TG_EVAL_DUALNET_TC) {
         if (!e->have_weights) return fail(TG_ERR_STATE, "tg_load_weights has not been called");

@@ -703,9 +703,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_snapshot_roots(Dev D)
     push_leaf<N>(D, g, gs, sm.root, s, gs[GS_COLOR], nullptr, 0, -1, lane);
 }
 
-// Test evaluator: the hash "network" of oracle.hashnet (exactly representable fp32 outputs), one warp per slot.
+// Test evaluators, one warp per slot: variant 0 = the hash "network" of oracle.hashnet (dyadic fp32 outputs: every sum of
+// them is exact in any order), variant 1 = oracle.hashnet2 (values k/1000, logits raw/1000 - 4: fp32 sums round, so the
+// queue-order fp32 accumulation of the backup is observable).
 template <int N>
-__global__ void __launch_bounds__(128) k_hashnet(const float* planes, const int* n_slots, int use_logit, float* policy, float* value)
+__global__ void __launch_bounds__(128) k_hashnet(const float* planes, const int* n_slots, int use_logit, float* policy, float* value, int variant)
 {
     using G = Geo<N>;
     const int slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = lane_id();
@@ -729,11 +731,15 @@ __global__ void __launch_bounds__(128) k_hashnet(const float* planes, const int*
     for (int i = lane; i < G::A; i += 32) {
         const u64 r = mix64(h + (u64)i);
         const float raw = (float)((r >> 40) & 0xFFFFull);
-        policy[(size_t)slot * G::A + i] = use_logit ? __fsub_rn(__fdiv_rn(raw, 8192.0f), 4.0f) : __fdiv_rn(raw, 1048576.0f);
+        if (variant == 0) policy[(size_t)slot * G::A + i] = use_logit ? __fsub_rn(__fdiv_rn(raw, 8192.0f), 4.0f) : __fdiv_rn(raw, 1048576.0f);
+        else policy[(size_t)slot * G::A + i] = use_logit ? __fsub_rn(__fdiv_rn(raw, 1000.0f), 4.0f) : __fdiv_rn(raw, 1000000.0f);
     }
     if (lane == 0) {
-        const float va = (float)(mix64(h + 1000ull) & 0xFFull), vb = (float)(mix64(h + 1001ull) & 0xFFull);
-        const float v0 = __fdiv_rn(va, 512.0f), v1 = __fdiv_rn(vb, 512.0f);
+        const u64 ra = mix64(h + 1000ull), rb = mix64(h + 1001ull);
+        const float va = variant == 0 ? (float)(ra & 0xFFull) : (float)(ra % 500ull);
+        const float vb = variant == 0 ? (float)(rb & 0xFFull) : (float)(rb % 500ull);
+        const float den = variant == 0 ? 512.0f : 1000.0f;
+        const float v0 = __fdiv_rn(va, den), v1 = __fdiv_rn(vb, den);
         value[(size_t)slot * 3 + 0] = v0; value[(size_t)slot * 3 + 1] = v1;
         value[(size_t)slot * 3 + 2] = __fsub_rn(__fsub_rn(1.0f, v0), v1);
     }

@@ -7,7 +7,7 @@ from . import _lib
 from ._lib import check
 
 MODE_SH, MODE_PUCT = 0, 1
-EVAL_DUALNET_TC, EVAL_DUALNET_FP32, EVAL_HASHNET = 0, 1, 2
+EVAL_DUALNET_TC, EVAL_DUALNET_FP32, EVAL_HASHNET, EVAL_HASHNET2 = 0, 1, 2, 3
 PASS, RESIGN = 0, -1
 BLACK, WHITE = 1, 2
 

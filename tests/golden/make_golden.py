@@ -12,6 +12,9 @@ parity tests need from it is recorded here and committed as small .npz files:
   dualnet_<N>.npz  DualNet outputs for seeded numpy weights on real planes (T2)
   analysis_9.npz   lz-analyze / cgos-analyze strings, PV lists and tree dumps of PUCT searches
   eye_table.npz    the 65 536-entry eye LUT of board/pattern.py
+  search2_<N>.npz  digest goldens at the full BASELINE budgets (19x19 PUCT-400 batch 1/8 + super-ko, SH-400, PUCT-1600
+                   batch 256), 13x13, and a NON-dyadic hash evaluator (fp32 queue-order value accumulation observable)
+  model_ref_9.bin  a model.bin written by the reference's save_model and read back by its load_network (+ .npz outputs)
 
 Usage:  python tests/golden/make_golden.py --size 9   (and --size 19)
         19x19 needs BOARD_SIZE patched in a private copy of the reference; the
@@ -28,6 +31,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.dont_write_bytecode = True
 
 
@@ -132,21 +136,21 @@ def gen_board(size, n_games, seed, out):
 
 
 class HashNet:
-    """Stands in for DualNet on both sides (oracle.hashnet): exact fp32 outputs."""
-    def __init__(self):
+    """Stands in for DualNet on both sides (oracle.hashnet: dyadic fp32 outputs; variant 1 = oracle.hashnet2: non-dyadic)."""
+    def __init__(self, variant=0):
         import torch
+        from oracle import oracle as orc
         self.torch = torch
         self.calls = 0
+        self.fn = orc.hashnet2 if variant else orc.hashnet
 
     def inference(self, x):
-        from oracle.oracle import hashnet
-        pol, val = hashnet(x.numpy(), False)
+        pol, val = self.fn(x.numpy(), False)
         self.calls += x.shape[0]
         return self.torch.from_numpy(pol), self.torch.from_numpy(val)
 
     def inference_with_policy_logits(self, x):
-        from oracle.oracle import hashnet
-        pol, val = hashnet(x.numpy(), True)
+        pol, val = self.fn(x.numpy(), True)
         self.calls += x.shape[0]
         return self.torch.from_numpy(pol), self.torch.from_numpy(val)
 
@@ -290,6 +294,109 @@ def gen_search(size, seed, out, sh_visits, puct_visits):
     np.savez_compressed(out, size=size, seed=seed, zobrist=np.asarray(hash_bit_mask, np.uint64),
                         movelist=np.array(ml_flat, np.int16), movelist_off=np.array(ml_off, np.int64), **packed)
     print(f"search golden: {len(cases)} cases -> {out}")
+
+
+def gen_search2(size, seed, out, n_positions, sh_cases, puct_cases, fixed_positions=None):
+    """Digest goldens (tests/golden_util.py DigestGolden): trees of searches at full BASELINE budgets.
+    sh_cases: [(visits, evaluator)], puct_cases: [(visits, batch, evaluator, strict)]; evaluator 0 = hashnet, 1 = hashnet2."""
+    import time
+    from board.go_board import GoBoard
+    from board.stone import Stone
+    from mcts.tree import MCTSTree
+    from mcts.time_manager import TimeManager, TimeControl
+    from golden_util import node_digest
+    patch = NoisePatch(seed=seed)
+    movelists = fixed_positions if fixed_positions is not None else positions_for_search(size, seed + 1, n_positions)
+    ml_flat, ml_off = [], [0]
+    for ml in movelists:
+        ml_flat += ml; ml_off.append(len(ml_flat))
+    metas, scal, fsum, digest, roots, improved = [], [], [], [], [], []
+    node_off = [0]
+
+    def f32_exact(a, what):
+        a = np.asarray(a, np.float64)
+        assert np.array_equal(a.astype(np.float32).astype(np.float64), a), f"{what} is not fp32-representable in the reference"
+        return a.astype(np.float32)
+
+    def record(meta, tree, ip):
+        nodes = dump_tree(tree)
+        for nd in nodes:
+            scal.append([nd["k"], nd["node_visits"], nd["virtual_loss"]])
+            fsum.append([f32_exact(nd["node_value_sum"], "node_value_sum"), f32_exact(nd["raw_value"], "raw_value")])
+            digest.append(node_digest(nd["action"], nd["cidx"], nd["visits"], nd["vl"], f32_exact(nd["vsum"], "children_value_sum"),
+                                      f32_exact(nd["value"], "children_value"), nd["policy"]))
+        node_off.append(node_off[-1] + len(nodes))
+        roots.append(nodes[0]); improved.append(np.asarray(ip, np.float64)); metas.append(meta)
+
+    for pi, ml in enumerate(movelists):
+        b = GoBoard(board_size=size, komi=7.0, check_superko=True)
+        color = Stone.BLACK
+        for p in ml:
+            b.put_stone(p, color); color = Stone.get_opponent_color(color)
+        for visits, ev in sh_cases:
+            t0 = time.time()
+            tree = MCTSTree(HashNet(ev), tree_size=4096)
+            patch.key(pi, b.moves)
+            tm = TimeManager(TimeControl.CONSTANT_PLAYOUT, constant_visits=visits)
+            mv = tree.generate_move_with_sequential_halving(b, color, tm, True)
+            record(dict(kind=0, pos_index=pi, visits=visits, batch=1, move=mv, color=color.value, evaluator=ev, strict=0),
+                   tree, tree.get_root().calculate_improved_policy())
+            print(f"  pos {pi} SH {visits} ev {ev}: {tree.num_nodes} nodes, {time.time() - t0:.1f} s")
+        for visits, batch, ev, strict in puct_cases:
+            t0 = time.time()
+            tree = MCTSTree(HashNet(ev), tree_size=4096, batch_size=batch)
+            patch.key(pi, b.moves)
+            tm = TimeManager(TimeControl.STRICT_PLAYOUT if strict else TimeControl.CONSTANT_PLAYOUT, constant_visits=visits)
+            mv = tree.search_best_move(b, color, tm, {})
+            record(dict(kind=1, pos_index=pi, visits=visits, batch=batch, move=mv, color=color.value, evaluator=ev, strict=int(strict)),
+                   tree, np.zeros(0))
+            print(f"  pos {pi} PUCT {visits} batch {batch} ev {ev} strict {strict}: {tree.num_nodes} nodes, root visits "
+                  f"{tree.get_root().node_visits}, {time.time() - t0:.1f} s")
+    out_d = {"case_" + k: np.array([m[k] for m in metas]) for k in metas[0]}
+    root_off = np.cumsum([0] + [r["k"] for r in roots])
+    for k in ("action", "cidx", "value", "visits", "policy", "vl", "vsum"):
+        out_d["root_" + k] = np.concatenate([r[k] for r in roots])
+    from board.zobrist_hash import hash_bit_mask
+    np.savez_compressed(out, size=size, seed=seed, zobrist=np.asarray(hash_bit_mask, np.uint64),
+                        movelist=np.array(ml_flat, np.int16), movelist_off=np.array(ml_off, np.int64),
+                        node_off=np.array(node_off, np.int64), node_scal=np.array(scal, np.int32),
+                        node_fsum=np.array(fsum, np.float32), node_digest=np.array(digest, np.uint64),
+                        root_off=root_off.astype(np.int64), improved=np.concatenate(improved),
+                        improved_off=np.cumsum([0] + [len(x) for x in improved]), **out_d)
+    print(f"search2 golden: {len(metas)} cases, {node_off[-1]} nodes -> {out}")
+
+
+def gen_modelbin(size, seed, board_npz, out_bin, out_npz):
+    """model.bin written by the reference's own save_model (nn/utility.py:80-87) from a seeded DualNet whose BatchNorm
+    statistics are non-trivial, re-read through the reference's load_network (nn/utility.py:139-159), and the logits /
+    softmax outputs of that loaded network on real positions."""
+    import torch
+    from nn.network.dual_net import DualNet
+    from nn.utility import save_model, load_network
+    torch.manual_seed(seed)
+    net = DualNet(torch.device("cpu"), board_size=size)
+    rs = np.random.RandomState(seed)
+    with torch.no_grad():
+        for name, buf in net.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(torch.from_numpy((rs.standard_normal(buf.shape) * 0.1).astype(np.float32)))
+            elif name.endswith("running_var"):
+                buf.copy_(torch.from_numpy(rs.uniform(0.5, 1.5, buf.shape).astype(np.float32)))
+            elif name.endswith("num_batches_tracked"):
+                buf.fill_(17)
+        for name, p in net.named_parameters():
+            if ".bn" in name or name.startswith("bn_layer"):
+                p.copy_(torch.from_numpy((rs.uniform(0.5, 1.5, p.shape) if name.endswith("weight")
+                                          else rs.standard_normal(p.shape) * 0.1).astype(np.float32)))
+    save_model(net, out_bin)
+    loaded = load_network(out_bin, False)
+    planes = np.load(board_npz)["planes"][:16]
+    x = torch.from_numpy(planes)
+    logits, _ = loaded.inference_with_policy_logits(x)
+    pol, val = loaded.inference(x)
+    np.savez_compressed(out_npz, size=size, seed=seed, planes=planes, logits=logits.numpy(), policy_softmax=pol.numpy(),
+                        value_softmax=val.numpy(), names=np.array(list(loaded.state_dict().keys())))
+    print(f"model.bin golden: {os.path.getsize(out_bin)} bytes, {planes.shape[0]} positions -> {out_bin}, {out_npz}")
 
 
 def gen_analysis(size, seed, out):
@@ -497,6 +604,21 @@ def main():
         gen_rldata(N, os.path.join(HERE, "selfplay_9.npz"), os.path.join(HERE, "rldata_9.npz"))
     if want("dualnet"):
         gen_dualnet(N, 31337, os.path.join(HERE, f"board_{N}.npz"), os.path.join(HERE, f"dualnet_{N}.npz"))
+    if want("search2"):
+        out = os.path.join(HERE, f"search2_{N}.npz")
+        if N == 9:      # non-dyadic evaluator at every budget the 9x9 goldens use (fp32 queue-order accumulation)
+            gen_search2(N, 78, out, 6, [(16, 1), (50, 1), (400, 1)], [(100, 1, 1, 0), (120, 8, 1, 0), (400, 8, 1, 1)])
+        elif N == 13:   # 13x13 had no reference pin at all
+            gen_search2(N, 79, out, 3, [(50, 0), (400, 1)], [(100, 1, 1, 0), (120, 8, 0, 0)])
+        else:           # BASELINE configs[3] (PUCT-400 + super-ko, batch 1 and 8), SH-400, configs[4] (PUCT-1600, batch 256)
+            ml = positions_for_search(N, 78, 2)
+            mid = positions_for_search(N, 80, 4)
+            fixed = [ml[0], ml[1], next(m for m in mid[1:] if len(m) >= 60)[:60]]
+            gen_search2(N, 80, out, 0, [(400, 1)], [(400, 1, 1, 0), (400, 8, 1, 0), (1600, 256, 1, 0), (1600, 256, 0, 1)],
+                        fixed_positions=fixed)
+    if want("modelbin") and N == 9:
+        gen_modelbin(N, 2026, os.path.join(HERE, "board_9.npz"), os.path.join(HERE, "model_ref_9.bin"),
+                     os.path.join(HERE, "model_ref_9.npz"))
 
 
 if __name__ == "__main__":

@@ -20,7 +20,7 @@ def tb():
     return tamago_b200
 
 
-@pytest.mark.parametrize("size", [9, 19])
+@pytest.mark.parametrize("size", [9, 13, 19])
 def test_board_states_match_reference_golden(golden_dir, tb, size):
     g = dict(np.load(os.path.join(golden_dir, f"board_{size}.npz")))
     moves, colors, counts, start = pack_games(g)
@@ -50,7 +50,7 @@ def test_board_states_match_reference_golden(golden_dir, tb, size):
     e.close()
 
 
-@pytest.mark.parametrize("size", [9, 19])
+@pytest.mark.parametrize("size", [9, 13, 19])
 def test_planes_match_reference_golden(golden_dir, tb, size):
     """Planes after a prefix of each golden game, against the sampled reference planes and the oracle for every game."""
     from oracle import oracle as orc
@@ -116,4 +116,43 @@ def test_random_games_vs_oracle(tb):
             assert np.array_equal(d["legal"][k, -1, ci], lm) and np.array_equal(d["cand"][k, -1, ci], cm)
             assert np.array_equal(d["satari"][k, -1, ci], sa) and np.array_equal(d["eye"][k, -1, ci], ey)
         assert int(d["score"][k, -1]) == b.count_score()
+    e.close()
+
+
+def _corpus_chunk(args):
+    from oracle import oracle as orc
+    size, seed, first, games, plies = args
+    return orc.random_games(size, orc.default_zobrist(size), seed, games, plies, p_pass=0.02, p_any_legal=0.35, first_game=first)
+
+
+@pytest.mark.parametrize("size,games,chunk", [(9, 10240, 2048), (19, 1024, 256)])
+def test_bulk_random_game_corpus_vs_oracle(tb, size, games, chunk):
+    """SURVEY 7 step 3 at scale: >= 10^4 9x9 and >= 10^3 19x19 random games, EVERY ply compared through a 64-bit digest of
+    the whole observable state (colours, liberties, sizes, ko, prisoners, hash, legality / self-atari / eye / candidate
+    masks of both colours, count_score).  The oracle plays the games (C, one process per host core) and digests each
+    ply; the engine replays the moves and its per-ply dump is digested with the numpy twin."""
+    import multiprocessing as mp
+    from oracle import oracle as orc
+    orc.build()
+    plies = 2 * size * size
+    procs = max(1, min(os.cpu_count() or 1, 32))
+    per = max(1, chunk // procs)
+    e = tb.Engine(board_size=size, games=chunk, max_visits=4, superko=True, evaluator=tb.EVAL_HASHNET)
+    e.set_zobrist(orc.default_zobrist(size))
+    total_plies = 0
+    with mp.get_context("fork").Pool(procs) as pool:
+        for c0 in range(0, games, chunk):
+            jobs = [(size, 77, c0 + j, min(per, chunk - j), plies) for j in range(0, chunk, per)]
+            parts = pool.map(_corpus_chunk, jobs)
+            moves = np.concatenate([p[0] for p in parts]); counts = np.concatenate([p[1] for p in parts])
+            dig = np.concatenate([p[2] for p in parts])
+            assert len(moves) == chunk
+            e.reset()
+            d = e.play(moves, counts, dump=True)
+            got = orc.ply_digest_np(d, size)
+            valid = np.arange(plies)[None, :] < counts[:, None]
+            bad = np.argwhere((got != dig) & valid)
+            assert len(bad) == 0, f"size {size}: first mismatch at game {c0 + bad[0][0]} ply {bad[0][1]} of {len(bad)}"
+            total_plies += int(counts.sum())
+    assert total_plies > games * size * 4
     e.close()

@@ -19,7 +19,7 @@ def _weights(size, seed):
     return numpy_weights(size, seed)
 
 
-@pytest.mark.parametrize("size", [9, 19])
+@pytest.mark.parametrize("size", [9, 13, 19])
 @pytest.mark.parametrize("evaluator", ["tc", "fp32"])
 def test_dualnet_matches_reference_golden(golden_dir, size, evaluator):
     import tamago_b200 as tb
@@ -164,3 +164,22 @@ def test_device_resident_forward_aliases_engine_buffers(golden_dir):
     with pytest.raises(Exception):
         e.forward_device(planes.shape[0] + 1)
     e.close()
+
+
+def test_model_bin_of_the_reference_through_load_network(golden_dir):
+    """north_star: "the model.bin checkpoint loader stays drop-in".  model_ref_9.bin was written by the reference's
+    save_model (nn/utility.py:80-87); load_network (139-159) -> inference / inference_with_policy_logits on the device
+    must give the outputs the reference's own loaded network produced (1e-4), and a missing file keeps a random init."""
+    import torch
+    from tamago_b200.nn.network import load_network
+    g = np.load(os.path.join(golden_dir, "model_ref_9.npz"))
+    net = load_network(os.path.join(golden_dir, "model_ref_9.bin"), True, board_size=9)
+    x = torch.from_numpy(g["planes"])
+    logits, val = net.inference_with_policy_logits(x)
+    pol, val2 = net.inference(x)
+    dl = np.abs(logits.numpy() - g["logits"]).max()
+    print(f"model.bin: max |dlogit| {dl:.3e}")
+    assert dl <= TOL and np.abs(val.numpy() - g["value_softmax"]).max() <= TOL
+    assert np.abs(pol.numpy() - g["policy_softmax"]).max() <= TOL and np.array_equal(val.numpy(), val2.numpy())
+    rnd = load_network("/nonexistent/model.bin", True, board_size=9)       # utility.py:152-155: failure is swallowed
+    assert np.abs(rnd.inference_with_policy_logits(x)[0].numpy() - g["logits"]).max() > 1e-2

@@ -28,7 +28,7 @@ def _replay(path, check):
     return len(g["pos"])
 
 
-@pytest.mark.parametrize("size", [9, 19])
+@pytest.mark.parametrize("size", [9, 13, 19])
 def test_board_state_matches_reference(golden_dir, size):
     path = os.path.join(golden_dir, f"board_{size}.npz")
     if not os.path.isfile(path):
@@ -60,7 +60,7 @@ def test_board_state_matches_reference(golden_dir, size):
     assert _replay(path, check) > 100
 
 
-@pytest.mark.parametrize("size", [9, 19])
+@pytest.mark.parametrize("size", [9, 13, 19])
 def test_planes_exact(golden_dir, size):
     path = os.path.join(golden_dir, f"board_{size}.npz")
     if not os.path.isfile(path):
@@ -83,3 +83,80 @@ def test_eye_table(golden_dir):
     mine = np.ctypeslib.as_array(orc.lib().tgo_eye_table(), shape=(65536,))
     assert np.array_equal(mine, eye)
     assert int((eye != 0).sum()) > 100
+
+
+def test_ply_digest_numpy_twin_and_bulk_corpus():
+    """The bulk differential corpus (oracle.random_games): the C digest of a ply equals its numpy twin applied to the
+    exported state, so the GPU test can digest the engine's dump with numpy and compare 10^4 games ply by ply."""
+    n = 9
+    zob = orc.default_zobrist(n)
+    mv, cnt, dig = orc.random_games(n, zob, seed=5, games=6, max_plies=160, p_any_legal=0.5)
+    assert cnt.min() > 20
+    for g in (0, 5):
+        b = orc.OracleBoard(n, 7.0, True, zob)
+        color = orc.BLACK
+        keys = {k: [] for k in ("color", "libs", "size", "scal", "hash", "legal", "satari", "eye", "cand", "score")}
+        for i in range(cnt[g]):
+            b.put_stone(int(mv[g, i]), color)
+            color = 3 - color
+            s = b.state()
+            keys["color"].append(s["color"]); keys["libs"].append(s["libs"]); keys["size"].append(s["size"])
+            keys["scal"].append([s["moves"], s["ko_pos"], s["ko_move"], *s["prisoner"]]); keys["hash"].append(np.uint64(s["hash"]))
+            a = [b.analyze(c) for c in (orc.BLACK, orc.WHITE)]
+            for j, k in enumerate(("legal", "satari", "eye", "cand")):
+                keys[k].append([x[j] for x in a])
+            keys["score"].append(b.count_score())
+            assert b.ply_digest() == int(dig[g, i])
+        d = {k: np.array(v) for k, v in keys.items()}
+        assert np.array_equal(orc.ply_digest_np(d, n), dig[g, :cnt[g]])
+    # the digest is sensitive to every field
+    d2 = {k: v.copy() for k, v in d.items()}
+    d2["libs"][3, 40] += 1
+    assert orc.ply_digest_np(d2, n)[3] != dig[g, 3]
+
+
+def _tromp_taylor_py(color, n):
+    """independent 20-line flood fill: area score Black - White"""
+    w = n + 2
+    seen, score = set(), 0
+    for y in range(1, n + 1):
+        for x in range(1, n + 1):
+            p = x + y * w
+            if color[p] == 1:
+                score += 1
+            elif color[p] == 2:
+                score -= 1
+            elif p not in seen:
+                region, reach, todo = 0, set(), [p]
+                seen.add(p)
+                while todo:
+                    q = todo.pop()
+                    region += 1
+                    for r in (q - w, q - 1, q + 1, q + w):
+                        if color[r] in (1, 2):
+                            reach.add(int(color[r]))
+                        elif color[r] == 0 and r not in seen:
+                            seen.add(r); todo.append(r)
+                if reach == {1}:
+                    score += region
+                elif reach == {2}:
+                    score -= region
+    return score
+
+
+@pytest.mark.parametrize("size", [9, 19])
+def test_tromp_taylor_oracle(golden_dir, size):
+    """the oracle's area scorer against an independent Python flood fill on every ply of the golden games,
+    plus how often it agrees with the reference's count_score (go_board.py:561-608, not a flood fill: SURVEY A.3 Q9)."""
+    agree = total = 0
+
+    def check(b, g, i, *_):
+        nonlocal agree, total
+        if i % 3:
+            return
+        tt = b.tromp_taylor()
+        assert tt == _tromp_taylor_py(b.state()["color"], size), f"ply {i}"
+        agree += tt == int(g["score"][i]); total += 1
+
+    _replay(os.path.join(golden_dir, f"board_{size}.npz"), check)
+    assert total > 50 and 0 < agree < total      # the two scorers differ on open positions and agree on settled ones
