@@ -46,6 +46,9 @@ typedef struct tg_config {
     int32_t cgos_mode;        /* MCTSTree(cgos_mode=...) */
     int32_t net_blocks;       /* DualNet residual blocks (nn/network/dual_net.py:26), default 6 */
     uint64_t seed;            /* seed of the counter-based Dirichlet/Gumbel stream */
+    int32_t record_ring;      /* 1: keep the SelfPlayRecord of every running game on the device (sgf/selfplay_record.py:45-64) */
+    int32_t scoring;          /* final score of finished games: 0 = GoBoard.count_score (go_board.py:561-608, the reference),
+                                 1 = Tromp-Taylor area scoring (the adjudication get_final_status.py:15-64 asks GNU Go for) */
 } tg_config;
 
 /* DualNet parameters: host fp32 arrays named as in DualNet.state_dict() (nn/network/dual_net.py:14-39).
@@ -125,7 +128,8 @@ int  tg_set_zobrist(tg_engine* e, const uint64_t* table);
 /* nn/utility.py:139-159 load_network: parameters of DualNet */
 int  tg_load_weights(tg_engine* e, const tg_weights* w);
 
-/* GoBoard.clear (go_board.py:111) for the games flagged in mask (NULL = all); game_ids key the noise stream */
+/* GoBoard.clear (go_board.py:111) for the games flagged in mask (NULL = all); game_ids key the noise stream.
+ * Asynchronous: the arguments are copied before the call returns, the reset is ordered on the engine's stream. */
 int  tg_reset(tg_engine* e, const uint8_t* mask, const uint64_t* game_ids, const uint8_t* never_resign);
 /* GoBoard.put_stone (go_board.py:131) for counts[g] moves of every game; colors NULL = alternate from the side to move */
 int  tg_play(tg_engine* e, const int16_t* moves, const uint8_t* colors, const int32_t* counts, int32_t stride, tg_ply_dump* dump);
@@ -146,10 +150,31 @@ int   tg_eval_buffers(tg_engine* e, float** planes, float** policy, float** valu
 int   tg_forward_device(tg_engine* e, int32_t n, int32_t use_logit);
 void* tg_stream(tg_engine* e);
 int   tg_sync(tg_engine* e);
+/* ordering between the engine's (non-blocking) stream and a caller's cudaStream_t, e.g. the torch stream that fills
+ * `planes`: tg_stream_wait makes engine work queued afterwards wait for what the caller has queued so far,
+ * tg_stream_signal makes caller work queued afterwards wait for the engine */
+int   tg_stream_wait(tg_engine* e, void* caller_stream);
+int   tg_stream_signal(tg_engine* e, void* caller_stream);
 
 /* MCTSTree.generate_move_with_sequential_halving (tree.py:318) / search_best_move (tree.py:57) for every game.
  * play = 1 additionally runs the body of selfplay_worker's move loop (worker.py:58-87). */
 int  tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t strict, int32_t play, tg_step_result* out);
+/* The same in two halves: tg_genmove_async queues the move of every game and returns at once (root_arrays = 1 also
+ * stages root.action / improved policy / visits for tg_collect); tg_collect waits for it and fills the result.  The
+ * host is free in between (format records, write files, prepare the next reset) while the GPU searches. */
+int  tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int32_t strict, int32_t play, int32_t root_arrays);
+int  tg_collect(tg_engine* e, tg_step_result* out);
+
+/* SelfPlayRecord of finished games (sgf/selfplay_record.py:45-110), kept per game on the device (tg_config.record_ring):
+ * tg_fetch_records queues the device->host copies of the listed games' records (call it after tg_collect and before the
+ * tg_reset that recycles their slots); tg_format_records returns their SGF texts back to back (offsets[n+1]);
+ * tg_write_records writes <dir>/<index[i]>.sgf for each (write_record, :67-110) and returns the number of moves written;
+ * tg_fetched_record exposes the raw arrays of one fetched game ([n_moves] and [n_moves][stride]). */
+int     tg_fetch_records(tg_engine* e, const int32_t* games, int32_t n);
+int64_t tg_format_records(tg_engine* e, char* buf, int64_t cap, int64_t* offsets);
+int64_t tg_write_records(tg_engine* e, const char* dir, const int64_t* index);
+int     tg_fetched_record(tg_engine* e, int32_t i, int32_t* n_moves, int16_t* move, uint8_t* color, int16_t* num_children,
+                          int16_t* action, double* improved);
 
 /* MCTSTree.node[index] of one game */
 int  tg_tree_size(tg_engine* e, int32_t game, int32_t* num_nodes);

@@ -17,7 +17,7 @@ class Config(C.Structure):
     _fields_ = [("board_size", C.c_int32), ("komi", C.c_float), ("superko", C.c_int32), ("games", C.c_int32),
                 ("max_visits", C.c_int32), ("batch_size", C.c_int32), ("max_nodes", C.c_int32), ("device", C.c_int32),
                 ("evaluator", C.c_int32), ("dedup", C.c_int32), ("cgos_mode", C.c_int32), ("net_blocks", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("record_ring", C.c_int32), ("scoring", C.c_int32)]
 
 
 class Weights(C.Structure):
@@ -63,6 +63,14 @@ EXPORTS = {
     "tg_stream": (C.c_void_p, [C.c_void_p]),
     "tg_sync": (C.c_int, [C.c_void_p]),
     "tg_genmove": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(StepResult)]),
+    "tg_genmove_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "tg_collect": (C.c_int, [C.c_void_p, C.POINTER(StepResult)]),
+    "tg_fetch_records": (C.c_int, [C.c_void_p, i32p, C.c_int32]),
+    "tg_format_records": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64, i64p]),
+    "tg_write_records": (C.c_int64, [C.c_void_p, C.c_char_p, i64p]),
+    "tg_fetched_record": (C.c_int, [C.c_void_p, C.c_int32, i32p, i16p, u8p, i16p, i16p, f64p]),
+    "tg_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tg_stream_signal": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_tree_size": (C.c_int, [C.c_void_p, C.c_int32, i32p]),
     "tg_read_node": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(NodeView)]),
     "tg_format_sgf": (C.c_int, [C.c_int32, C.c_int32, i32p, i32p, i32p, i16p, f64p, C.c_int32, C.c_int32, C.c_int32,

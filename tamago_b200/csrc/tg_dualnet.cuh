@@ -238,13 +238,13 @@ constexpr int BND_WARP = 7;               // rows 224..255: the tail of tile 1, 
 
 template <int N, int G>
 __global__ void __launch_bounds__(TC_THREADS, 1)       // 21 warps -> 6 on one scheduler -> 80 registers per thread
-k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__ n_slots_ptr, int use_logit,
+k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__ n_slots_ptr, int n_direct, int use_logit,
              float* __restrict__ policy, float* __restrict__ value)
 {
     using NG = NetGeo<N, G>;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_slots = *n_slots_ptr;
+    const int n_slots = n_slots_ptr ? *n_slots_ptr : n_direct;     // device-side count (search) or launch argument (tg_forward*)
     const int ngroups = (n_slots + G - 1) / G;
     const int L = 1 + 2 * P.blocks;
 

@@ -12,8 +12,23 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 using namespace tg;
+
+// host-side fan-out for record formatting / file output (a few worker threads; the GPU runs the next step meanwhile)
+template <class F> static void parallel_for(int n, F&& f)
+{
+    if (n <= 0) return;
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int nt = std::max(1, std::min(std::min(n, 16), hw > 1 ? hw - 1 : 1));
+    if (nt == 1) { for (int i = 0; i < n; i++) f(i); return; }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&] { for (int i; (i = next.fetch_add(1)) < n;) f(i); });
+    for (auto& t : th) t.join();
+}
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -37,8 +52,18 @@ struct tg_engine {
     int simt_chunk = 0;
     // host staging (pinned)
     int* h_gs = nullptr; int16_t* h_action = nullptr; double* h_improved = nullptr; int* h_visits = nullptr;
+    // tg_reset staging: pinned host block + device block, sized once (nothing is allocated on the hot path)
+    unsigned char* h_reset = nullptr; unsigned char* d_reset = nullptr; cudaEvent_t ev_reset = nullptr; bool reset_pending = false;
+    // asynchronous step state (tg_genmove_async -> tg_collect)
+    bool step_pending = false, step_arrays = false; cudaEvent_t ev_step = nullptr;
+    // finished-game records fetched from the device ring (tg_fetch_records -> tg_format_records / tg_write_records)
+    struct Fetched { int game, n_moves, winner, resigned; float score; size_t off; };
+    std::vector<Fetched> fetched; unsigned char* h_rec = nullptr; size_t h_rec_cap = 0; cudaEvent_t ev_rec = nullptr; bool rec_pending = false;
+    int rec_row_bytes = 0;
+    cudaEvent_t ev_x = nullptr;                  // cross-stream ordering with a caller's stream
     bool have_weights = false, have_zobrist = false;
     int64_t launches = 0;
+    int n_eval_events = 2;
     float last_ms = 0.f, last_eval_ms = 0.f;
     int64_t last_eval_slots = 0;
     int sms = 148;
@@ -227,6 +252,16 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     DA(D.planes, (size_t)e->slot_cap * e->PLANES); DA(D.policy, (size_t)e->slot_cap * e->A); DA(D.value, (size_t)e->slot_cap * 3);
     DA(D.n_slots, 1);
     DA(D.out_action, (size_t)games * e->AP); DA(D.out_improved, (size_t)games * e->AP); DA(D.out_visits, (size_t)games * e->AP);
+    if (cfg->record_ring) {                       // per-game record of the running game (SelfPlayRecord), rows = move limit
+        const size_t rows = (size_t)games * 2 * e->NN;
+        D.rec_moves = 2 * e->NN;
+        DA(D.rec_move, rows); DA(D.rec_color, rows); DA(D.rec_k, rows); DA(D.rec_action, rows * e->AP); DA(D.rec_improved, rows * e->AP);
+    }
+    {
+        void* q = nullptr;
+        if (cudaMalloc(&q, (size_t)games * 10) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "reset staging"));
+        e->allocs.push_back(q); e->d_reset = reinterpret_cast<unsigned char*>(q);
+    }
     {
         u64* z; uint8_t* eye;
         DA(z, (size_t)4 * e->CELLS); DA(eye, 65536);
@@ -248,8 +283,12 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     if (cudaMallocHost(&e->h_gs, (size_t)games * GS_STRIDE * sizeof(int)) != cudaSuccess ||
         cudaMallocHost(&e->h_action, (size_t)games * e->AP * sizeof(int16_t)) != cudaSuccess ||
         cudaMallocHost(&e->h_improved, (size_t)games * e->AP * sizeof(double)) != cudaSuccess ||
-        cudaMallocHost(&e->h_visits, (size_t)games * e->AP * sizeof(int)) != cudaSuccess)
+        cudaMallocHost(&e->h_visits, (size_t)games * e->AP * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&e->h_reset, (size_t)games * 10) != cudaSuccess)
         return bail(fail(TG_ERR_CUDA, "pinned host allocation failed"));
+    if (cudaEventCreateWithFlags(&e->ev_reset, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_rec, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_x, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(TG_ERR_CUDA, "event"));
 
     DISPATCH_N(e, rc = setup_kernel_attrs<BN>());
     if (rc) return bail(rc);
@@ -284,6 +323,9 @@ extern "C" void tg_engine_destroy(tg_engine* e)
     if (e->h_action) cudaFreeHost(e->h_action);
     if (e->h_improved) cudaFreeHost(e->h_improved);
     if (e->h_visits) cudaFreeHost(e->h_visits);
+    if (e->h_reset) cudaFreeHost(e->h_reset);
+    if (e->h_rec) cudaFreeHost(e->h_rec);
+    for (cudaEvent_t ev : {e->ev_reset, e->ev_step, e->ev_rec, e->ev_x}) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -412,19 +454,24 @@ extern "C" int tg_reset(tg_engine* e, const uint8_t* mask, const uint64_t* game_
     if (!e) return fail(TG_ERR_ARG, "null engine");
     CK(cudaSetDevice(e->cfg.device));
     const int games = e->cfg.games;
-    uint8_t *d_mask = nullptr, *d_nr = nullptr; u64* d_ids = nullptr;
-    std::vector<u64> ids(games);
-    for (int g = 0; g < games; g++) ids[g] = game_ids ? game_ids[g] : (u64)g;
-    CK(cudaMalloc(&d_ids, (size_t)games * 8));
-    CK(cudaMemcpyAsync(d_ids, ids.data(), (size_t)games * 8, cudaMemcpyHostToDevice, e->stream));
-    if (mask) { CK(cudaMalloc(&d_mask, games)); CK(cudaMemcpyAsync(d_mask, mask, games, cudaMemcpyHostToDevice, e->stream)); }
-    if (never_resign) { CK(cudaMalloc(&d_nr, games)); CK(cudaMemcpyAsync(d_nr, never_resign, games, cudaMemcpyHostToDevice, e->stream)); }
+    // staging block [ids u64 x games | mask u8 x games | never_resign u8 x games]: the previous reset's upload must have
+    // left the pinned block before it is rewritten (one event wait, normally long past)
+    if (e->reset_pending) { CK(cudaEventSynchronize(e->ev_reset)); e->reset_pending = false; }
+    u64* h_ids = reinterpret_cast<u64*>(e->h_reset);
+    uint8_t* h_mask = e->h_reset + (size_t)games * 8; uint8_t* h_nr = h_mask + games;
+    for (int g = 0; g < games; g++) h_ids[g] = game_ids ? game_ids[g] : (u64)g;
+    if (mask) memcpy(h_mask, mask, games);
+    if (never_resign) memcpy(h_nr, never_resign, games);
+    CK(cudaMemcpyAsync(e->d_reset, e->h_reset, (size_t)games * 10, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaEventRecord(e->ev_reset, e->stream));
+    e->reset_pending = true;
+    const u64* d_ids = reinterpret_cast<const u64*>(e->d_reset);
+    const uint8_t* d_mask = mask ? e->d_reset + (size_t)games * 8 : nullptr;
+    const uint8_t* d_nr = never_resign ? e->d_reset + (size_t)games * 9 : nullptr;
     DISPATCH_N(e, (k_reset<BN><<<search_grid(e), SEARCH_WARPS * 32, search_smem(BN), e->stream>>>(e->D, d_mask, d_ids, d_nr)));
     e->launches++;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(e->stream));
-    cudaFree(d_ids); if (d_mask) cudaFree(d_mask); if (d_nr) cudaFree(d_nr);
-    return TG_OK;
+    return TG_OK;                                   // asynchronous: ordered before everything queued on the engine's stream later
 }
 
 extern "C" int tg_set_to_move(tg_engine* e, const int32_t* colors)
@@ -440,28 +487,34 @@ extern "C" int tg_set_to_move(tg_engine* e, const int32_t* colors)
 extern "C" int tg_play(tg_engine* e, const int16_t* moves, const uint8_t* colors, const int32_t* counts, int32_t stride, tg_ply_dump* dump)
 {
     if (!e || !moves || !counts || stride < 1) return fail(TG_ERR_ARG, "bad argument");
-    CK(cudaSetDevice(e->cfg.device));
     const int games = e->cfg.games;
-    const size_t nm = (size_t)games * stride;
-    int16_t* d_moves = nullptr; uint8_t* d_colors = nullptr; int* d_counts = nullptr;
-    CK(cudaMalloc(&d_moves, nm * 2)); CK(cudaMalloc(&d_counts, (size_t)games * 4));
-    CK(cudaMemcpyAsync(d_moves, moves, nm * 2, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(d_counts, counts, (size_t)games * 4, cudaMemcpyHostToDevice, e->stream));
-    if (colors) { CK(cudaMalloc(&d_colors, nm)); CK(cudaMemcpyAsync(d_colors, colors, nm, cudaMemcpyHostToDevice, e->stream)); }
-    PlyDump pd{}; std::vector<void*> tmp;
     const int plies = dump ? dump->plies : 0;
+    if (dump && plies < 1) return fail(TG_ERR_ARG, "dump->plies must be positive");
+    for (int g = 0; g < games; g++) {
+        if (counts[g] < 0 || counts[g] > stride) return fail(TG_ERR_ARG, "counts[g] outside [0, stride]");
+        if (dump && counts[g] > plies) return fail(TG_ERR_ARG, "dump->plies smaller than counts[g]");
+    }
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t nm = (size_t)games * stride;
+    std::vector<void*> tmp;                         // every temporary is released on every exit path
+    struct Guard { std::vector<void*>& v; ~Guard() { for (void* p : v) cudaFree(p); } } guard{tmp};
+    auto da = [&](void** p, size_t bytes) { if (cudaMalloc(p, std::max<size_t>(bytes, 1)) != cudaSuccess) return 1; tmp.push_back(*p); return 0; };
+    int16_t* d_moves = nullptr; uint8_t* d_colors = nullptr; int* d_counts = nullptr;
+    int bad = da((void**)&d_moves, nm * 2) | da((void**)&d_counts, (size_t)games * 4);
+    if (colors) bad |= da((void**)&d_colors, nm);
+    PlyDump pd{};
     const size_t np = (size_t)games * std::max(plies, 1);
     if (dump) {
-        if (plies < 1) return fail(TG_ERR_ARG, "dump->plies must be positive");
-        auto da = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return 1; tmp.push_back(*p); return 0; };
-        int bad = 0;
         bad |= da((void**)&pd.color, np * e->CELLS); bad |= da((void**)&pd.libs, np * e->CELLS * 2); bad |= da((void**)&pd.size, np * e->CELLS * 2);
         bad |= da((void**)&pd.scal, np * 5 * 4); bad |= da((void**)&pd.hash, np * 8);
         bad |= da((void**)&pd.legal, np * 2 * e->NN); bad |= da((void**)&pd.satari, np * 2 * e->NN * 2);
         bad |= da((void**)&pd.eye, np * 2 * e->NN); bad |= da((void**)&pd.cand, np * 2 * e->NN); bad |= da((void**)&pd.score, np * 4);
-        if (bad) { for (void* p : tmp) cudaFree(p); return fail(TG_ERR_CUDA, "dump allocation failed"); }
         pd.stride = plies;
     }
+    if (bad) return fail(TG_ERR_CUDA, "temporary allocation failed");
+    CK(cudaMemcpyAsync(d_moves, moves, nm * 2, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(d_counts, counts, (size_t)games * 4, cudaMemcpyHostToDevice, e->stream));
+    if (colors) CK(cudaMemcpyAsync(d_colors, colors, nm, cudaMemcpyHostToDevice, e->stream));
     DISPATCH_N(e, (k_play<BN><<<search_grid(e), SEARCH_WARPS * 32, search_smem(BN), e->stream>>>(e->D, d_moves, d_colors, d_counts, stride, pd, dump ? 1 : 0)));
     e->launches++;
     CK(cudaGetLastError());
@@ -473,19 +526,20 @@ extern "C" int tg_play(tg_engine* e, const int16_t* moves, const uint8_t* colors
 #undef CP_OUT
     }
     CK(cudaStreamSynchronize(e->stream));
-    for (void* p : tmp) cudaFree(p);
-    cudaFree(d_moves); cudaFree(d_counts); if (d_colors) cudaFree(d_colors);
     return TG_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // evaluator: slot bases, feature planes, network (device-side slot count; no host round trip)
 // ---------------------------------------------------------------------------------------------
-template <int BN> static int launch_net(tg_engine* e, int use_logit, int max_slots)
+// n_direct < 0: the slot count is read from device memory (written by k_scan); otherwise it is a launch argument, so that
+// back-to-back tg_forward_device calls cannot race on a staged count.
+template <int BN> static int launch_net(tg_engine* e, int use_logit, int max_slots, int n_direct = -1)
 {
     const Dev& D = e->D;
+    const int* n_ptr = n_direct < 0 ? D.n_slots : nullptr;
     if (e->cfg.evaluator == TG_EVAL_HASHNET || e->cfg.evaluator == TG_EVAL_HASHNET2) {
-        k_hashnet<BN><<<(max_slots + 3) / 4, 128, 0, e->stream>>>(D.planes, D.n_slots, use_logit, D.policy, D.value,
+        k_hashnet<BN><<<(max_slots + 3) / 4, 128, 0, e->stream>>>(D.planes, n_ptr, n_direct, use_logit, D.policy, D.value,
                                                                   e->cfg.evaluator == TG_EVAL_HASHNET2 ? 1 : 0);
         e->launches++;
     } else if (e->cfg.evaluator == TG_EVAL_DUALNET_TC) {
@@ -493,14 +547,16 @@ template <int BN> static int launch_net(tg_engine* e, int use_logit, int max_slo
         constexpr int G = TcGroup<BN>::G;
         const int groups = (max_slots + G - 1) / G;
         const int grid = std::max(1, std::min(e->sms, groups));
-        k_dualnet_tc<BN, G><<<grid, TC_THREADS, NetGeo<BN, G>::SMEM_BYTES, e->stream>>>(e->net, D.planes, D.n_slots, use_logit, D.policy, D.value);
+        k_dualnet_tc<BN, G><<<grid, TC_THREADS, NetGeo<BN, G>::SMEM_BYTES, e->stream>>>(e->net, D.planes, n_ptr, n_direct, use_logit, D.policy, D.value);
         e->launches++;
     } else {
         if (!e->have_weights) return fail(TG_ERR_STATE, "tg_load_weights has not been called");
         // the CUDA-core path needs the slot count on the host (reference path only)
-        int n = 0;
-        CK(cudaMemcpyAsync(&n, D.n_slots, 4, cudaMemcpyDeviceToHost, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
+        int n = n_direct;
+        if (n_direct < 0) {
+            CK(cudaMemcpyAsync(&n, D.n_slots, 4, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaStreamSynchronize(e->stream));
+        }
         const int L = 1 + 2 * e->net.blocks;
         const int smem = 64 * (BN + 2) * (BN + 2) * 4;
         for (int s0 = 0; s0 < n; s0 += e->simt_chunk) {
@@ -539,9 +595,11 @@ template <int BN> static int launch_eval(tg_engine* e, int use_logit, int max_sl
     return 0;
 }
 
-extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t strict, int32_t play, tg_step_result* out)
+// Queue one move of every game on the engine's stream (no host synchronisation); tg_collect waits for it.
+extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int32_t strict, int32_t play, int32_t root_arrays)
 {
     if (!e) return fail(TG_ERR_ARG, "null engine");
+    if (e->step_pending) return fail(TG_ERR_STATE, "a step is already in flight: call tg_collect first");
     if (visits < 1 || visits > e->cfg.max_visits) return fail(TG_ERR_ARG, "visits outside [1, max_visits]");
     if (mode != TG_MODE_SH && mode != TG_MODE_PUCT) return fail(TG_ERR_ARG, "bad mode");
     CK(cudaSetDevice(e->cfg.device));
@@ -591,12 +649,28 @@ extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t st
     if (rc) return rc;
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->events[1], e->stream));
-    // results -> pinned staging -> caller
+    e->n_eval_events = ev;
+    // results -> pinned staging (the caller's buffers are filled by tg_collect)
     CK(cudaMemcpyAsync(e->h_gs, D.gs, (size_t)games * GS_STRIDE * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    if (out && out->action) CK(cudaMemcpyAsync(e->h_action, D.out_action, (size_t)games * e->AP * 2, cudaMemcpyDeviceToHost, e->stream));
-    if (out && out->improved) CK(cudaMemcpyAsync(e->h_improved, D.out_improved, (size_t)games * e->AP * 8, cudaMemcpyDeviceToHost, e->stream));
-    if (out && out->visits) CK(cudaMemcpyAsync(e->h_visits, D.out_visits, (size_t)games * e->AP * 4, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    if (root_arrays) {
+        CK(cudaMemcpyAsync(e->h_action, D.out_action, (size_t)games * e->AP * 2, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_improved, D.out_improved, (size_t)games * e->AP * 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemcpyAsync(e->h_visits, D.out_visits, (size_t)games * e->AP * 4, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaEventRecord(e->ev_step, e->stream));
+    e->step_pending = true; e->step_arrays = root_arrays != 0;
+    return TG_OK;
+}
+
+extern "C" int tg_collect(tg_engine* e, tg_step_result* out)
+{
+    if (!e) return fail(TG_ERR_ARG, "null engine");
+    if (!e->step_pending) return fail(TG_ERR_STATE, "no step in flight");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaEventSynchronize(e->ev_step));
+    e->step_pending = false;
+    const int games = e->cfg.games;
+    Dev& D = e->D;
     if (D.prof) {
         long long h[16];
         CK(cudaMemcpy(h, D.prof, sizeof h, cudaMemcpyDeviceToHost));
@@ -606,7 +680,7 @@ extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t st
     }
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
     e->last_eval_ms = 0.f;
-    for (int i = 2; i + 1 < ev; i += 2) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->events[i], e->events[i + 1])); e->last_eval_ms += ms; }
+    for (int i = 2; i + 1 < e->n_eval_events; i += 2) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->events[i], e->events[i + 1])); e->last_eval_ms += ms; }
     int64_t evals = 0, uevals = 0; int any_err = 0;
     for (int g = 0; g < games; g++) {
         const int* gs = e->h_gs + (size_t)g * GS_STRIDE;
@@ -624,6 +698,8 @@ extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t st
     }
     e->last_eval_slots = uevals;
     if (out) {
+        if ((out->action || out->improved || out->visits) && !e->step_arrays)
+            return fail(TG_ERR_STATE, "root arrays were not requested from tg_genmove_async");
         if (out->action) memcpy(out->action, e->h_action, (size_t)games * e->AP * 2);
         if (out->improved) memcpy(out->improved, e->h_improved, (size_t)games * e->AP * 8);
         if (out->visits) memcpy(out->visits, e->h_visits, (size_t)games * e->AP * 4);
@@ -631,6 +707,149 @@ extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t st
     }
     if (any_err && !(out && out->error)) return fail(TG_ERR_SEARCH, "search error flags set (history/depth/node/queue overflow); pass tg_step_result.error to inspect");
     return TG_OK;
+}
+
+extern "C" int tg_genmove(tg_engine* e, int32_t mode, int32_t visits, int32_t strict, int32_t play, tg_step_result* out)
+{
+    const int arrays = out && (out->action || out->improved || out->visits);
+    const int rc = tg_genmove_async(e, mode, visits, strict, play, arrays);
+    return rc ? rc : tg_collect(e, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finished-game records: rows of the device ring -> pinned staging -> SGF text / files (C++ writer, tg_record.cpp).
+//   tg_fetch_records queues the copies on the engine's stream, i.e. BEFORE a later tg_reset / tg_genmove_async can reuse
+//   the rows; tg_format_records / tg_write_records wait for them and run on the host while the GPU already works on
+//   the next step.
+// ---------------------------------------------------------------------------------------------
+extern "C" int tg_fetch_records(tg_engine* e, const int32_t* games_list, int32_t n)
+{
+    if (!e || n < 0 || (n > 0 && !games_list)) return fail(TG_ERR_ARG, "bad argument");
+    if (!e->D.rec_moves) return fail(TG_ERR_STATE, "engine was created without record_ring");
+    if (e->step_pending) return fail(TG_ERR_STATE, "collect the step in flight first");
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->rec_pending) { CK(cudaEventSynchronize(e->ev_rec)); e->rec_pending = false; }
+    const Dev& D = e->D;
+    const int AP = e->AP, MM = D.rec_moves;
+    e->fetched.clear();
+    size_t total = 0;
+    for (int i = 0; i < n; i++) {
+        const int g = games_list[i];
+        if (g < 0 || g >= e->cfg.games) return fail(TG_ERR_ARG, "game index out of range");
+        const int* gs = e->h_gs + (size_t)g * GS_STRIDE;                   // state block of the last collected step
+        tg_engine::Fetched f;
+        f.game = g; f.n_moves = std::min(gs[GS_NMOVES], MM); f.winner = gs[GS_WINNER]; f.resigned = gs[GS_RESIGNED];
+        memcpy(&f.score, &gs[GS_SCORE], 4);
+        f.off = total;
+        total += ((size_t)f.n_moves * (2 + 1 + 2 + (size_t)AP * 10) + 15) & ~(size_t)15;
+        e->fetched.push_back(f);
+    }
+    if (total > e->h_rec_cap) {
+        if (e->h_rec) cudaFreeHost(e->h_rec);
+        e->h_rec = nullptr; e->h_rec_cap = 0;
+        const size_t want = std::max<size_t>(total + total / 2, (size_t)1 << 20);
+        CK(cudaMallocHost(&e->h_rec, want));
+        e->h_rec_cap = want;
+    }
+    for (const auto& f : e->fetched) {
+        if (f.n_moves == 0) continue;
+        const size_t m = (size_t)f.n_moves, r0 = (size_t)f.game * MM;
+        unsigned char* p = e->h_rec + f.off;                               // [improved f64 m*AP | action i16 m*AP | move i16 m | k i16 m | color u8 m]
+        CK(cudaMemcpyAsync(p, D.rec_improved + r0 * AP, m * AP * 8, cudaMemcpyDeviceToHost, e->stream)); p += m * AP * 8;
+        CK(cudaMemcpyAsync(p, D.rec_action + r0 * AP, m * AP * 2, cudaMemcpyDeviceToHost, e->stream)); p += m * AP * 2;
+        CK(cudaMemcpyAsync(p, D.rec_move + r0, m * 2, cudaMemcpyDeviceToHost, e->stream)); p += m * 2;
+        CK(cudaMemcpyAsync(p, D.rec_k + r0, m * 2, cudaMemcpyDeviceToHost, e->stream)); p += m * 2;
+        CK(cudaMemcpyAsync(p, D.rec_color + r0, m, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaEventRecord(e->ev_rec, e->stream));
+    e->rec_pending = true;
+    return TG_OK;
+}
+
+int tg_record_text(int n, int n_moves, const int16_t* moves, const uint8_t* colors, const int16_t* ks, const int16_t* action,
+                   const double* improved, int stride, int winner, int resigned, double score, double komi, std::string& out);
+
+static int wait_records(tg_engine* e)
+{
+    if (e->rec_pending) { CK(cudaEventSynchronize(e->ev_rec)); e->rec_pending = false; }
+    return 0;
+}
+
+static void record_text_of(const tg_engine* e, const tg_engine::Fetched& f, std::string& out)
+{
+    const size_t m = (size_t)f.n_moves, AP = (size_t)e->AP;
+    const unsigned char* p = e->h_rec + f.off;
+    const double* improved = reinterpret_cast<const double*>(p); p += m * AP * 8;
+    const int16_t* action = reinterpret_cast<const int16_t*>(p); p += m * AP * 2;
+    const int16_t* mv = reinterpret_cast<const int16_t*>(p); p += m * 2;
+    const int16_t* ks = reinterpret_cast<const int16_t*>(p); p += m * 2;
+    const uint8_t* col = p;
+    tg_record_text(e->N, f.n_moves, mv, col, ks, action, improved, e->AP, f.winner, f.resigned, (double)f.score, (double)e->cfg.komi, out);
+}
+
+// raw arrays of fetched record i (tests, training-data emitters on the host)
+extern "C" int tg_fetched_record(tg_engine* e, int32_t i, int32_t* n_moves, int16_t* move, uint8_t* color, int16_t* num_children,
+                                 int16_t* action, double* improved)
+{
+    if (!e || i < 0 || i >= (int)e->fetched.size()) return fail(TG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(e->cfg.device));
+    int rc = wait_records(e); if (rc) return rc;
+    const auto& f = e->fetched[i];
+    const size_t m = (size_t)f.n_moves, AP = (size_t)e->AP;
+    const unsigned char* p = e->h_rec + f.off;
+    if (n_moves) *n_moves = f.n_moves;
+    if (improved) memcpy(improved, p, m * AP * 8);
+    p += m * AP * 8;
+    if (action) memcpy(action, p, m * AP * 2);
+    p += m * AP * 2;
+    if (move) memcpy(move, p, m * 2);
+    p += m * 2;
+    if (num_children) memcpy(num_children, p, m * 2);
+    p += m * 2;
+    if (color) memcpy(color, p, m);
+    return TG_OK;
+}
+
+// SGF text of every fetched game, concatenated; offsets[i]..offsets[i+1] delimit game i.  Returns the total size, or
+// the size needed (as a negative number minus one is never used: the call fails with TG_ERR_ARG when cap is too small
+// and tg_last_error names the size).
+extern "C" int64_t tg_format_records(tg_engine* e, char* buf, int64_t cap, int64_t* offsets)
+{
+    if (!e || !buf || !offsets) return fail(TG_ERR_ARG, "null argument");
+    cudaSetDevice(e->cfg.device);
+    if (wait_records(e)) return TG_ERR_CUDA;
+    const int n = (int)e->fetched.size();
+    std::vector<std::string> texts(n);
+    parallel_for(n, [&](int i) { record_text_of(e, e->fetched[i], texts[i]); });
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) { offsets[i] = total; total += (int64_t)texts[i].size(); }
+    offsets[n] = total;
+    if (total > cap) return fail(TG_ERR_ARG, "buffer too small: need " + std::to_string(total) + " bytes");
+    for (int i = 0; i < n; i++) memcpy(buf + offsets[i], texts[i].data(), texts[i].size());
+    return total;
+}
+
+// sgf/selfplay_record.py:104-108: write <dir>/<index[i]>.sgf for every fetched game (formatting and file output on
+// host worker threads).  Returns the number of root moves recorded in the files.
+extern "C" int64_t tg_write_records(tg_engine* e, const char* dir, const int64_t* index)
+{
+    if (!e || !dir || !index) return fail(TG_ERR_ARG, "null argument");
+    cudaSetDevice(e->cfg.device);
+    if (wait_records(e)) return TG_ERR_CUDA;
+    const int n = (int)e->fetched.size();
+    std::vector<int> bad(n, 0);
+    parallel_for(n, [&](int i) {
+        std::string text;
+        record_text_of(e, e->fetched[i], text);
+        const std::string path = std::string(dir) + "/" + std::to_string((long long)index[i]) + ".sgf";
+        FILE* fp = fopen(path.c_str(), "wb");
+        if (!fp) { bad[i] = 1; return; }
+        if (fwrite(text.data(), 1, text.size(), fp) != text.size()) bad[i] = 1;
+        if (fclose(fp) != 0) bad[i] = 1;
+    });
+    int64_t moves = 0;
+    for (int i = 0; i < n; i++) { if (bad[i]) return fail(TG_ERR_ARG, "could not write a record file under " + std::string(dir)); moves += e->fetched[i].n_moves; }
+    return moves;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -667,12 +886,29 @@ extern "C" int tg_forward_device(tg_engine* e, int32_t n, int32_t use_logit)
 {
     if (!e || n < 0 || n > e->slot_cap) return fail(TG_ERR_ARG, "n outside [0, slot_cap]");
     CK(cudaSetDevice(e->cfg.device));
-    // the slot count is read by the kernel from device memory: stage it through the engine's pinned block
-    e->h_gs[0] = n;
-    CK(cudaMemcpyAsync(e->D.n_slots, e->h_gs, 4, cudaMemcpyHostToDevice, e->stream));
+    // the slot count travels as a launch argument: back-to-back calls need no synchronisation between them
     int rc = 0;
-    DISPATCH_N(e, rc = launch_net<BN>(e, use_logit, n));
+    DISPATCH_N(e, rc = launch_net<BN>(e, use_logit, n, n));
     return rc;
+}
+
+// Cross-stream ordering for the zero-copy buffers: the engine's stream is non-blocking, so work a caller queued on ITS
+// stream (e.g. torch filling `planes`) is ordered with the engine's only through these two calls.
+extern "C" int tg_stream_wait(tg_engine* e, void* caller_stream)      // engine work queued after this call waits for the caller's stream
+{
+    if (!e) return fail(TG_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaEventRecord(e->ev_x, (cudaStream_t)caller_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_x, 0));
+    return TG_OK;
+}
+extern "C" int tg_stream_signal(tg_engine* e, void* caller_stream)    // caller work queued after this call waits for the engine's stream
+{
+    if (!e) return fail(TG_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaEventRecord(e->ev_x, e->stream));
+    CK(cudaStreamWaitEvent((cudaStream_t)caller_stream, e->ev_x, 0));
+    return TG_OK;
 }
 
 extern "C" void* tg_stream(tg_engine* e) { return e ? (void*)e->stream : nullptr; }
@@ -694,10 +930,8 @@ extern "C" int tg_forward(tg_engine* e, const float* planes, int32_t n, int32_t 
     for (int s0 = 0; s0 < n; s0 += e->slot_cap) {
         const int ns = std::min(e->slot_cap, n - s0);
         CK(cudaMemcpyAsync(D.planes, planes + (size_t)s0 * e->PLANES, (size_t)ns * e->PLANES * 4, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(D.n_slots, &ns, 4, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaStreamSynchronize(e->stream));                       // &ns is a stack variable
         int rc = 0;
-        DISPATCH_N(e, rc = launch_net<BN>(e, use_logit, ns));
+        DISPATCH_N(e, rc = launch_net<BN>(e, use_logit, ns, ns));
         if (rc) return rc;
         CK(cudaMemcpyAsync(policy + (size_t)s0 * e->A, D.policy, (size_t)ns * e->A * 4, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaMemcpyAsync(value + (size_t)s0 * 3, D.value, (size_t)ns * 3 * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -729,7 +963,10 @@ extern "C" int tg_read_node(tg_engine* e, int32_t game, int32_t index, tg_node_v
     RD(action, t.action, int16_t); RD(children_index, t.cidx, int); RD(children_value, t.cval, float); RD(children_visits, t.cvis, int);
     RD(children_policy, t.cpol, double); RD(children_virtual_loss, t.cvl, int); RD(children_value_sum, t.cvsum, float);
 #undef RD
-    if (o->noise) CK(cudaMemcpyAsync(o->noise, t.noise + (size_t)game * e->AP, (size_t)e->AP * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (o->noise) {                                             // MCTSNode.noise: the Gumbel draw lives on the root only (node.py:57, 275-278)
+        if (index == 0) CK(cudaMemcpyAsync(o->noise, t.noise + (size_t)game * e->AP, (size_t)e->AP * 8, cudaMemcpyDeviceToHost, e->stream));
+        else memset(o->noise, 0, (size_t)e->AP * 8);
+    }
     CK(cudaStreamSynchronize(e->stream));
     o->num_children = hdr[H_K]; o->node_visits = hdr[H_NV]; o->virtual_loss = hdr[H_VL];
     memcpy(&o->node_value_sum, &hdr[H_VSUM], 4); memcpy(&o->raw_value, &hdr[H_RAW], 4);
@@ -749,13 +986,11 @@ extern "C" int tg_bench_kernel(tg_engine* e, const char* name, int32_t slots, in
     if (k == "eval_ms") { *ms_out = e->last_eval_ms; return TG_OK; }
     if (k == "eval_slots") { *ms_out = (float)e->last_eval_slots; return TG_OK; }
     if (k == "dualnet") {
-        CK(cudaMemcpyAsync(e->D.n_slots, &slots, 4, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
         int rc = 0;
-        DISPATCH_N(e, rc = launch_net<BN>(e, 1, slots));            // warm-up
+        DISPATCH_N(e, rc = launch_net<BN>(e, 1, slots, slots));     // warm-up
         if (rc) return rc;
         CK(cudaEventRecord(e->events[0], e->stream));
-        for (int i = 0; i < iters && !rc; i++) DISPATCH_N(e, rc = launch_net<BN>(e, 1, slots));
+        for (int i = 0; i < iters && !rc; i++) DISPATCH_N(e, rc = launch_net<BN>(e, 1, slots, slots));
         if (rc) return rc;
         CK(cudaEventRecord(e->events[1], e->stream));
         CK(cudaStreamSynchronize(e->stream));
@@ -768,12 +1003,10 @@ extern "C" int tg_bench_kernel(tg_engine* e, const char* name, int32_t slots, in
         long long* d = nullptr;
         CK(cudaMalloc(&d, 64 * 8));
         CK(cudaMemset(d, 0, 64 * 8));
-        CK(cudaMemcpyAsync(e->D.n_slots, &slots, 4, cudaMemcpyHostToDevice, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
         NetDev saved = e->net;
         e->net.dbg = d;
         int rc = 0;
-        DISPATCH_N(e, rc = launch_net<BN>(e, 1, slots));
+        DISPATCH_N(e, rc = launch_net<BN>(e, 1, slots, slots));
         e->net = saved;
         if (rc) return rc;
         CK(cudaStreamSynchronize(e->stream));

@@ -52,6 +52,13 @@ struct Dev {
     int16_t* out_action;     // [games][AP]
     double* out_improved;    // [games][AP]
     int* out_visits;         // [games][AP]
+    // per-game record ring (sgf/selfplay_record.py:45-64 save_record): one row per root move of the running game
+    int rec_moves;           // rows per game (2 N^2, the move limit of selfplay/worker.py:44); 0 = no ring
+    int16_t* rec_move;       // [games][rec_moves]
+    uint8_t* rec_color;      // [games][rec_moves]
+    int16_t* rec_k;          // [games][rec_moves]      root.get_num_children()
+    int16_t* rec_action;     // [games][rec_moves][AP]  root.action
+    double* rec_improved;    // [games][rec_moves][AP]  root.calculate_improved_policy()
     // constants
     const u64* zob; const uint8_t* eye;
     long long* prof;         // optional clock64 accumulators of game 0 (development: TG_PROF=1)
@@ -566,6 +573,14 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_move_end(Dev D, int mode,
         if (lane == 0) { gs[GS_WINNER] = opp(color); gs[GS_RESIGNED] = 1; gs[GS_FINISHED] = 1; gs[GS_SCORE] = __float_as_int(0.0f); }
         return;
     }
+    if (D.rec_moves > 0 && gs[GS_NMOVES] < D.rec_moves) {                        // worker.py:72 record.save_record(root, pos, color)
+        const size_t r = (size_t)g * D.rec_moves + gs[GS_NMOVES];
+        for (int i = lane; i < G::AP; i += 32) {
+            D.rec_action[r * G::AP + i] = i < k ? t.action[i] : (int16_t)0;
+            D.rec_improved[r * G::AP + i] = i < k ? sm.s0[i] : 0.0;
+        }
+        if (lane == 0) { D.rec_move[r] = (int16_t)move; D.rec_color[r] = (uint8_t)color; D.rec_k[r] = (int16_t)k; }
+    }
     BScal s;
     wb_load<N>(sm.root, s, pool_of<N>(D), g, lane);
     wb_put_stone<N>(sm.root, s, move, color, D.zob, D.hist_hash + (size_t)g * G::MAXREC, D.hist_pos + (size_t)g * G::MAXREC, lane);
@@ -707,11 +722,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_snapshot_roots(Dev D)
 // them is exact in any order), variant 1 = oracle.hashnet2 (values k/1000, logits raw/1000 - 4: fp32 sums round, so the
 // queue-order fp32 accumulation of the backup is observable).
 template <int N>
-__global__ void __launch_bounds__(128) k_hashnet(const float* planes, const int* n_slots, int use_logit, float* policy, float* value, int variant)
+__global__ void __launch_bounds__(128) k_hashnet(const float* planes, const int* n_slots, int n_direct, int use_logit, float* policy, float* value, int variant)
 {
     using G = Geo<N>;
     const int slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = lane_id();
-    if (slot >= *n_slots) return;
+    if (slot >= (n_slots ? *n_slots : n_direct)) return;
     const float* pl = planes + (size_t)slot * G::PLANES;
     u64 h = 0;
     for (int j = lane; j < G::PLANES; j += 32) {

@@ -18,15 +18,16 @@ def _ptr(a, ct):
 
 class Engine:
     def __init__(self, board_size=9, games=1, max_visits=400, komi=7.0, superko=True, batch_size=1, max_nodes=0,
-                 device=0, evaluator=EVAL_DUALNET_TC, dedup=False, cgos_mode=False, net_blocks=6, seed=0):
+                 device=0, evaluator=EVAL_DUALNET_TC, dedup=False, cgos_mode=False, net_blocks=6, seed=0,
+                 record_ring=False, scoring=0):
         self.lib = _lib.load()
         self.n, self.games = board_size, games
         self.nn, self.A = board_size * board_size, board_size * board_size + 1
         self.cells = (board_size + 2) ** 2
         self.stride = self.lib.tg_action_stride(board_size)
-        self.komi, self.net_blocks = komi, net_blocks
+        self.komi, self.net_blocks, self.device = komi, net_blocks, device
         cfg = _lib.Config(board_size, komi, int(superko), games, max_visits, batch_size, max_nodes, device,
-                          evaluator, int(dedup), int(cgos_mode), net_blocks, seed)
+                          evaluator, int(dedup), int(cgos_mode), net_blocks, seed, int(record_ring), int(scoring))
         h = C.c_void_p()
         check(self.lib.tg_engine_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -132,13 +133,20 @@ class Engine:
         class _View:
             def __init__(self, ptr, shape):
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev = torch.device("cuda", self.device)
         mk = lambda ptr, shape: torch.as_tensor(_View(ptr.value, shape), device=dev)
         return (mk(p, (cap.value, 6, self.n, self.n)), mk(q, (cap.value, self.A)), mk(v, (cap.value, 3)))
 
-    def forward_device(self, n, use_logit=True):
-        """DualNet on the first n slots of the device batch, asynchronous on the engine's stream (see sync / stream)."""
+    def forward_device(self, n, use_logit=True, torch_stream=None):
+        """DualNet on the first n slots of the device batch, asynchronous on the engine's stream (see sync / stream).
+        With torch_stream (a torch.cuda.Stream) the call is ordered after what that stream has queued (the fill of
+        `planes`) and the stream's later work waits for the outputs: no host synchronisation on either side."""
+        cs = None if torch_stream is None else C.c_void_p(torch_stream.cuda_stream)
+        if cs is not None:
+            check(self.lib.tg_stream_wait(self.h, cs))
         check(self.lib.tg_forward_device(self.h, int(n), int(use_logit)))
+        if cs is not None:
+            check(self.lib.tg_stream_signal(self.h, cs))
 
     @property
     def stream(self):
@@ -148,6 +156,66 @@ class Engine:
         check(self.lib.tg_sync(self.h))
 
     # -- search -----------------------------------------------------------------------------------
+    def genmove_async(self, mode=MODE_SH, visits=400, strict=False, play=False, full=False):
+        """Queue one move of every game and return at once; collect() waits for it."""
+        self._pending_full = bool(full)
+        check(self.lib.tg_genmove_async(self.h, mode, visits, int(strict), int(play), int(full)))
+
+    def collect(self):
+        g, s = self.games, self.stride
+        full = getattr(self, "_pending_full", False)
+        r = dict(move=np.zeros(g, np.int32), color=np.zeros(g, np.int32), num_children=np.zeros(g, np.int32),
+                 finished=np.zeros(g, np.int32), winner=np.zeros(g, np.int32), resigned=np.zeros(g, np.int32),
+                 score=np.zeros(g, np.float32), error=np.zeros(g, np.int32), evals=np.zeros(2, np.int64))
+        if full:
+            r.update(action=np.zeros((g, s), np.int16), improved=np.zeros((g, s), np.float64), visits=np.zeros((g, s), np.int32))
+        sr = _lib.StepResult()
+        ct = dict(move=C.c_int32, color=C.c_int32, num_children=C.c_int32, action=C.c_int16, improved=C.c_double,
+                  visits=C.c_int32, finished=C.c_int32, winner=C.c_int32, resigned=C.c_int32, score=C.c_float,
+                  error=C.c_int32, evals=C.c_int64)
+        for k, v in r.items():
+            setattr(sr, k, _ptr(v, ct[k]))
+        check(self.lib.tg_collect(self.h, C.byref(sr)))
+        return r
+
+    # -- records of finished games (device ring -> SGF) ---------------------------------------------
+    def fetch_records(self, games):
+        gl = np.ascontiguousarray(games, dtype=np.int32)
+        self._n_fetched = len(gl)
+        check(self.lib.tg_fetch_records(self.h, _ptr(gl, C.c_int32), len(gl)))
+
+    def format_records(self):
+        """SGF text of every fetched game (sgf/selfplay_record.py:67-110)."""
+        n = getattr(self, "_n_fetched", 0)
+        off = np.zeros(n + 1, np.int64)
+        cap = 1 << 16
+        while True:
+            buf = C.create_string_buffer(cap)
+            rc = self.lib.tg_format_records(self.h, buf, cap, _ptr(off, C.c_int64))
+            if rc >= 0:
+                break
+            if int(off[n]) > cap:
+                cap = int(off[n]) + 16
+                continue
+            check(int(rc))
+        return [buf.raw[off[i]:off[i + 1]].decode("utf-8") for i in range(n)]
+
+    def write_records(self, save_dir, index):
+        """<save_dir>/<index[i]>.sgf for every fetched game; returns the number of moves written."""
+        idx = np.ascontiguousarray(index, dtype=np.int64)
+        assert len(idx) == getattr(self, "_n_fetched", 0)
+        return int(check(self.lib.tg_write_records(self.h, str(save_dir).encode(), _ptr(idx, C.c_int64))))
+
+    def fetched_record(self, i):
+        n = C.c_int32()
+        check(self.lib.tg_fetched_record(self.h, i, C.byref(n), None, None, None, None, None))
+        m, s = n.value, self.stride
+        mv, col, k = np.zeros(m, np.int16), np.zeros(m, np.uint8), np.zeros(m, np.int16)
+        act, imp = np.zeros((m, s), np.int16), np.zeros((m, s), np.float64)
+        check(self.lib.tg_fetched_record(self.h, i, C.byref(n), _ptr(mv, C.c_int16), _ptr(col, C.c_uint8), _ptr(k, C.c_int16),
+                                         _ptr(act, C.c_int16), _ptr(imp, C.c_double)))
+        return dict(move=mv, color=col, num_children=k, action=act, improved=imp)
+
     def genmove(self, mode=MODE_SH, visits=400, strict=False, play=False, full=True):
         g, s = self.games, self.stride
         r = dict(move=np.zeros(g, np.int32), color=np.zeros(g, np.int32), num_children=np.zeros(g, np.int32),

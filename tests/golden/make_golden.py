@@ -388,12 +388,16 @@ def gen_modelbin(size, seed, board_npz, out_bin, out_npz):
             if ".bn" in name or name.startswith("bn_layer"):
                 p.copy_(torch.from_numpy((rs.uniform(0.5, 1.5, p.shape) if name.endswith("weight")
                                           else rs.standard_normal(p.shape) * 0.1).astype(np.float32)))
+        # keep both heads alive (a negative BatchNorm shift would zero them behind the ReLU and the test would only see the FC bias)
+        net.policy_head.bn_layer.bias.copy_(torch.tensor([0.6, 0.4]))
+        net.value_head.bn_layer.bias.copy_(torch.tensor([0.5]))
     save_model(net, out_bin)
     loaded = load_network(out_bin, False)
     planes = np.load(board_npz)["planes"][:16]
     x = torch.from_numpy(planes)
     logits, _ = loaded.inference_with_policy_logits(x)
     pol, val = loaded.inference(x)
+    assert logits.numpy().std(axis=0).min() > 1e-3 and val.numpy().std(axis=0).min() > 1e-4, "dead head: outputs do not depend on the position"
     np.savez_compressed(out_npz, size=size, seed=seed, planes=planes, logits=logits.numpy(), policy_softmax=pol.numpy(),
                         value_softmax=val.numpy(), names=np.array(list(loaded.state_dict().keys())))
     print(f"model.bin golden: {os.path.getsize(out_bin)} bytes, {planes.shape[0]} positions -> {out_bin}, {out_npz}")

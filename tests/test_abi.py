@@ -73,3 +73,34 @@ def test_sgf_writer_matches_reference_text(golden_dir):
             score = 0.0 if resigned else float(re_field[2:]) * (1 if winner == 1 else -1)
         out = tamago_b200.format_sgf(n, moves, colors, ks, np.array(acts), np.array(imps), winner, resigned, score, komi)
         assert out == text
+
+
+def test_fast_policy_formatting_equals_printf():
+    """The record writer formats ~10^7 improved-policy values per pool turn-over with its own "%.3e" (tg_record.cpp
+    fmt_3e).  It must be byte-identical to the reference's f"{p:.3e}" (sgf/selfplay_record.py:61): random values over
+    every magnitude the softmax produces, values next to rounding boundaries, exact ties, zeros and denormals."""
+    import numpy as np
+    import tamago_b200
+    rs = np.random.RandomState(12)
+    vals = [rs.uniform(0, 1, 60000), 10.0 ** rs.uniform(-30, 0, 60000), 10.0 ** rs.uniform(-320, -290, 2000),
+            np.array([0.0, 1.0, 0.5, 0.25, 0.015625, 0.0009765625, 1e-18, 9.9995e-5, 9.99949999e-5, 0.99995, 0.999949999999,
+                      1.2345e-3, 1.2355e-3, 5e-324, 1e-19, 1.0000000000000002e-19, 123456.0, 12345.0, 1e15, 2e15])]
+    # values constructed to sit within a few ulp of a 4-digit rounding boundary
+    d = rs.randint(1000, 10000, 40000) + 0.5
+    e = rs.randint(-25, 0, 40000)
+    near = d * 10.0 ** (e - 3.0)
+    vals += [near, np.nextafter(near, 0), np.nextafter(near, 1), near * (1 + 1e-9), near * (1 - 1e-9)]
+    x = np.concatenate(vals)
+    per = 90
+    rows = (len(x) + per - 1) // per
+    pad = np.zeros(rows * per)
+    pad[:len(x)] = x
+    imp = np.zeros((rows, 96))
+    imp[:, :per] = pad.reshape(rows, per)
+    act = np.zeros((rows, 96), np.int16)
+    text = tamago_b200.format_sgf(9, [0] * rows, [1] * rows, [per] * rows, act, imp, 3, 0, 0.0, 7.0)
+    got = re.findall(r"pass:([^ \]]+)", text)
+    assert len(got) == rows * per
+    want = [f"{v:.3e}" for v in pad]
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, bad[:5]

@@ -159,3 +159,65 @@ def test_c1_one_game_puct100_through_the_dropin_loop():
             break
     assert moves == [int(p) for p in want["pos"]]
     assert len(moves) > 20
+
+
+def test_async_step_and_record_ring(golden_dir):
+    """tg_genmove_async / tg_collect / tg_fetch_records / tg_format_records: the golden self-play games again, driven
+    through the asynchronous API with the records taken from the device ring instead of per-step root arrays."""
+    import tamago_b200 as tb
+    g = np.load(os.path.join(golden_dir, "selfplay_9.npz"))
+    size, seed, visits = int(g["size"]), int(g["seed"]), int(g["visits"])
+    ng = len(g["sgf"])
+    e = tb.Engine(board_size=size, games=ng, max_visits=visits, superko=True, evaluator=tb.EVAL_HASHNET, seed=seed, record_ring=True)
+    e.set_zobrist(g["zobrist"])
+    e.reset(game_ids=np.arange(ng), never_resign=g["never_resign"])
+    texts = {}
+    e.genmove_async(mode=tb.MODE_SH, visits=visits, play=True)
+    with pytest.raises(Exception):
+        e.genmove_async(mode=tb.MODE_SH, visits=visits, play=True)        # one step in flight at a time
+    for _ in range(2 * size * size + 2):
+        r = e.collect()
+        fin = [k for k in range(ng) if r["finished"][k] and k not in texts]
+        if fin:
+            e.fetch_records(fin)
+        if len(texts) + len(fin) < ng:
+            e.genmove_async(mode=tb.MODE_SH, visits=visits, play=True)    # next step runs while the records are formatted
+        if fin:
+            for k, t in zip(fin, e.format_records()):
+                texts[k] = t
+            rec = e.fetched_record(0)
+            want = g["moves"][g["moves_off"][fin[0]]:g["moves_off"][fin[0] + 1]]
+            assert np.array_equal(rec["move"], want) and rec["action"].shape == (len(want), e.stride)
+        if len(texts) == ng:
+            break
+    assert len(texts) == ng
+    for k in range(ng):
+        assert texts[k] == str(g["sgf"][k]), f"game {k}"
+    e.close()
+
+
+def test_forward_device_back_to_back_and_stream_ordering(golden_dir):
+    """two tg_forward_device calls without a sync in between must not race on the slot count, and the engine's
+    stream must be ordered with the torch stream that fills the aliased planes (tg_stream_wait / tg_stream_signal)."""
+    import torch
+    import tamago_b200 as tb
+    from tamago_b200.nn.utility import random_init_state_dict
+    g = np.load(os.path.join(golden_dir, "dualnet_9.npz"))
+    x = g["planes"]
+    e = tb.Engine(board_size=9, games=64, max_visits=32, evaluator=tb.EVAL_DUALNET_TC)
+    e.load_state_dict(random_init_state_dict(9, 1))
+    ref_p, ref_v = e.forward(x, use_logit=True)
+    planes, policy, value = e.eval_tensors()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for rep in range(20):
+            n1, n2 = len(x), 3
+            policy.zero_(); value.zero_()
+            planes[:n1].copy_(torch.from_numpy(x).cuda(non_blocking=True), non_blocking=True)
+            e.forward_device(n1, use_logit=True, torch_stream=st)          # no host synchronisation anywhere
+            p1 = policy[:n1].clone()
+            e.forward_device(n2, use_logit=True, torch_stream=st)          # a smaller count right behind the first call
+            p2 = policy[:n1].clone()
+        st.synchronize()
+    assert np.array_equal(p1.cpu().numpy(), ref_p) and np.array_equal(p2.cpu().numpy(), ref_p)
+    e.close()
