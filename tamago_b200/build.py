@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtamago_b200.so")
 SOURCES = ["tg_engine.cu", "tg_record.cpp"]
-HEADERS = ["tg_common.cuh", "tg_detmath.cuh", "tg_board.cuh", "tg_tree.cuh", "tg_search.cuh", "tg_dualnet.cuh",
+HEADERS = ["tg_common.cuh", "tg_detmath.cuh", "tg_board.cuh", "tg_tree.cuh", "tg_search.cuh", "tg_block.cuh", "tg_dualnet.cuh",
            os.path.join("..", "..", "include", "tamago_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               # search math must round like numpy/torch scalar arithmetic: no FMA contraction (the DualNet

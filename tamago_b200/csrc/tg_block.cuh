@@ -1,0 +1,608 @@
+// tg_block.cuh -- block-per-game PUCT search: one CTA of NT threads walks one game's tree.
+//
+// Reference path: MCTSTree.search / search_mcts (mcts/tree.py:130-174, 199-244), select_next_action
+// (mcts/node.py:141-157, mcts/pucb/pucb.py:8-29), expand_node (tree.py:247-270), process_mini_batch (tree.py:273-315),
+// TimeManager.is_move_decided (mcts/time_manager.py:146-163), GoBoard.put_stone / is_legal (board/go_board.py:131-304).
+//
+// Why a block: descents of one PUCT batch are sequentially dependent (each one changes the virtual losses the next
+// selection reads), so the only parallelism inside a game is INSIDE a ply -- the 362-child selection sweep, the
+// board sweeps of put_stone, the 361-point legality analysis of an expansion, the 362-prior Dirichlet draw.  The
+// warp-per-game kernels (tg_search.cuh) run those 32 wide; with few games per GPU (BASELINE configs[3]: 1024 games,
+// configs[4]: ONE game) almost every warp slot of the machine is idle and a move is latency bound.  Here the same
+// steps run NT wide (NT = 256: 1024 games are one resident wave of 8 CTAs per SM) with block barriers in place of warp
+// barriers.  Results are bit-identical to the warp kernels: same float64 operations per child, same first-index
+// tie break, same summation orders (the Dirichlet normaliser keeps the "warp shape" of expand_node in tg_search.cuh).
+//
+// The backup of a batch is split the same way: priors of all evaluated nodes are scattered by the whole block (they
+// are independent), then one warp applies the values leaf by leaf in queue order (fp32 sums are order dependent).
+#pragma once
+#include "tg_search.cuh"
+
+namespace tg {
+
+template <int N, int NT> struct BlkSmem {
+    using G = Geo<N>;
+    static constexpr int NW = NT / 32;
+    static constexpr int CH = (G::NN + NT - 1) / NT;      // analysis points per thread
+    WBoard<N> root;
+    WBoard<N> scratch;
+    alignas(16) WAnalysis<N> an;                           // expansion scratch; selection stages child rows here
+    alignas(16) double s0[G::AP];                          // selection: priors; expansion: super-ko hit hashes, then -log u
+    double s1[G::AP];                                      // expansion: points of the super-ko hits (int16)
+    // reductions (ping-pong: one barrier per reduction)
+    u64 r_x[2][NW]; int r_i[2][NW]; int r_j[2][NW]; double r_d[2][NW];
+    int wcnt[NW];
+    int nhit;
+    double bc_d;
+    uint8_t flag[(G::NN + 15) & ~15];                      // expansion: candidate flags / super-ko verdicts per point
+};
+
+template <int NT> struct Blk {
+    int tid, lane, warp, ph;
+    __device__ __forceinline__ Blk() : tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), ph(0) {}
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+// ---- block reductions: warp shuffle, one shared slot per warp, every thread folds the NW slots -------------------
+template <int N, int NT>
+__device__ __forceinline__ void blk_xor_sum(BlkSmem<N, NT>& sm, Blk<NT>& k, u64& x, int& cnt)
+{
+    x = warp_xor64(x); cnt = warp_sum_i(cnt);
+    const int p = k.ph; k.ph ^= 1;
+    if (k.lane == 0) { sm.r_x[p][k.warp] = x; sm.r_i[p][k.warp] = cnt; }
+    k.sync();
+    u64 xx = 0; int cc = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) { xx ^= sm.r_x[p][w]; cc += sm.r_i[p][w]; }
+    x = xx; cnt = cc;
+}
+template <int N, int NT>
+__device__ __forceinline__ int blk_max_i(BlkSmem<N, NT>& sm, Blk<NT>& k, int v)
+{
+    v = warp_max_i(v);
+    const int p = k.ph; k.ph ^= 1;
+    if (k.lane == 0) sm.r_i[p][k.warp] = v;
+    k.sync();
+    int m = sm.r_i[p][0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; w++) m = max(m, sm.r_i[p][w]);
+    return m;
+}
+template <int N, int NT>
+__device__ __forceinline__ void blk_sum_max(BlkSmem<N, NT>& sm, Blk<NT>& k, int& s, int& mx)
+{
+    s = warp_sum_i(s); mx = warp_max_i(mx);
+    const int p = k.ph; k.ph ^= 1;
+    if (k.lane == 0) { sm.r_i[p][k.warp] = s; sm.r_j[p][k.warp] = mx; }
+    k.sync();
+    int ss = 0, mm = sm.r_j[p][0];
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) { ss += sm.r_i[p][w]; mm = max(mm, sm.r_j[p][w]); }
+    s = ss; mx = mm;
+}
+// argmax with numpy semantics (first index wins ties); idx = INT_MAX marks an empty thread
+template <int N, int NT>
+__device__ __forceinline__ int blk_argmax_d(BlkSmem<N, NT>& sm, Blk<NT>& k, double v, int idx)
+{
+    warp_argmax_d(v, idx);
+    const int p = k.ph; k.ph ^= 1;
+    if (k.lane == 0) { sm.r_d[p][k.warp] = v; sm.r_i[p][k.warp] = idx; }
+    k.sync();
+    double bv = sm.r_d[p][0]; int bi = sm.r_i[p][0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; w++) {
+        const double ov = sm.r_d[p][w]; const int oi = sm.r_i[p][w];
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    return bi;
+}
+template <int N, int NT>
+__device__ __forceinline__ int blk_min_i(BlkSmem<N, NT>& sm, Blk<NT>& k, int v)
+{
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int p = k.ph; k.ph ^= 1;
+    if (k.lane == 0) sm.r_i[p][k.warp] = v;
+    k.sync();
+    int m = sm.r_i[p][0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; w++) m = min(m, sm.r_i[p][w]);
+    return m;
+}
+
+// ---- board ------------------------------------------------------------------------------------------------------
+template <int N, int NT> __device__ inline void bb_recount(WBoard<N>& b, const Blk<NT>& k)
+{
+    using G = Geo<N>;
+    for (int c = k.tid; c < G::CP; c += NT) b.ls[c] = 0;
+    k.sync();
+    for (int c = k.tid; c < G::CELLS; c += NT) {
+        const int col = b.color[c];
+        if (col == BLACK || col == WHITE) atomicAdd(&b.ls[b.chain[c]], 1u);
+        else if (col == EMPTY) {
+            const int q[4] = { c - G::W, c - 1, c + 1, c + G::W };
+            int seen[4], ns = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int cc = b.color[q[i]];
+                if (cc != BLACK && cc != WHITE) continue;
+                const int l = b.chain[q[i]];
+                bool dup = false;
+                for (int j = 0; j < ns; j++) dup |= (seen[j] == l);
+                if (!dup) { seen[ns++] = l; atomicAdd(&b.ls[l], 1u << 16); }
+            }
+        }
+    }
+    k.sync();
+}
+
+template <int N, int NT>
+__device__ inline void bb_load(WBoard<N>& b, BScal& s, const BoardPool<N>& pool, int g, const Blk<NT>& k)
+{
+    using G = Geo<N>;
+    const uint32_t* c4 = reinterpret_cast<const uint32_t*>(pool.color + (size_t)g * G::CP);
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(b.color);
+    for (int i = k.tid; i < G::CP / 4; i += NT) d4[i] = c4[i];
+    const uint32_t* h2 = reinterpret_cast<const uint32_t*>(pool.chain + (size_t)g * G::CP);
+    uint32_t* e2 = reinterpret_cast<uint32_t*>(b.chain);
+    for (int i = k.tid; i < G::CP / 2; i += NT) e2[i] = h2[i];
+    for (int i = k.tid; i < BLOOM_WORDS; i += NT) b.bloom[i] = pool.bloom[(size_t)g * BLOOM_WORDS + i];
+    const int* sc = pool.scal + (size_t)g * 8;
+    s.hash = pool.hash[g];
+    s.moves = sc[0]; s.ko_pos = sc[1]; s.ko_move = sc[2]; s.pris0 = sc[3]; s.pris1 = sc[4];
+    k.sync();
+    bb_recount<N, NT>(b, k);
+}
+
+template <int N, int NT> __device__ inline void bb_copy(WBoard<N>& dst, const WBoard<N>& src, const Blk<NT>& k)
+{
+    static_assert(sizeof(WBoard<N>) % 4 == 0, "word copy");
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+    for (int i = k.tid; i < (int)(sizeof(WBoard<N>) / 4); i += NT) d[i] = a[i];
+    k.sync();
+}
+
+// GoBoard.put_stone (go_board.py:131-185); same steps as wb_put_stone, sweeps NT wide
+template <int N, int NT>
+__device__ inline void bb_put_stone(BlkSmem<N, NT>& sm, WBoard<N>& b, BScal& s, int pos, int color, const u64* __restrict__ zob,
+                                    u64* hist_hash, int16_t* hist_pos, Blk<NT>& k)
+{
+    using G = Geo<N>;
+    if (pos == PASS) {                                       // :138-141
+        if (k.tid == 0 && s.moves < G::MAXREC) { hist_hash[s.moves] = s.hash; hist_pos[s.moves] = 0; }
+        s.moves++;
+        k.sync();
+        return;
+    }
+    const int other = opp(color);
+    const int q[4] = { pos - G::W, pos - 1, pos + 1, pos + G::W };
+    int cap[4], ncap = 0, own[4], nown = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int cc = b.color[q[i]];
+        if (cc != color && cc != other) continue;
+        const int l = b.chain[q[i]];
+        if (cc == color) {
+            bool dup = false;
+            for (int j = 0; j < nown; j++) dup |= (own[j] == l);
+            if (!dup) own[nown++] = l;
+        } else if ((b.ls[l] >> 16) == 1u) {
+            bool dup = false;
+            for (int j = 0; j < ncap; j++) dup |= (cap[j] == l);
+            if (!dup) cap[ncap++] = l;
+        }
+    }
+    const int label = nown > 0 ? own[0] : pos;
+    k.sync();                                                // every thread has read the neighbourhood
+    if (k.tid == 0) { b.color[pos] = (uint8_t)color; b.chain[pos] = (uint16_t)label; }
+    s.hash ^= zob[color * G::CELLS + pos];
+    int prisoner = 0;
+    if (ncap > 0 || nown > 1) {
+        u64 hx = 0; int cnt = 0;
+        for (int c = k.tid; c < G::CELLS; c += NT) {
+            const int cc = b.color[c];
+            if (cc == other) {
+                const int l = b.chain[c];
+                bool hit = false;
+                for (int j = 0; j < ncap; j++) hit |= (cap[j] == l);
+                if (hit) { b.color[c] = EMPTY; hx ^= zob[other * G::CELLS + c]; cnt++; }
+            } else if (cc == color && c != pos) {
+                const int l = b.chain[c];
+                bool hit = false;
+                for (int j = 1; j < nown; j++) hit |= (own[j] == l);
+                if (hit) b.chain[c] = (uint16_t)label;
+            }
+        }
+        blk_xor_sum<N, NT>(sm, k, hx, cnt);                  // (contains a barrier)
+        s.hash ^= hx;
+        prisoner = cnt;
+    }
+    if (color == BLACK) s.pris0 += prisoner; else s.pris1 += prisoner;
+    k.sync();
+    if (ncap == 0 && nown <= 1) {
+        if (k.tid == 0) {                                    // local liberty update, see wb_put_stone
+            int el[4], ne = 0;
+            unsigned gained = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int cc = b.color[q[i]];
+                if (cc == other) {
+                    const int l = b.chain[q[i]];
+                    bool dup = false;
+                    for (int j = 0; j < ne; j++) dup |= (el[j] == l);
+                    if (!dup) { el[ne++] = l; b.ls[l] -= 1u << 16; }
+                } else if (cc == EMPTY) {
+                    bool already = false;
+                    if (nown == 1) {
+                        const int r[4] = { q[i] - G::W, q[i] - 1, q[i] + 1, q[i] + G::W };
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            already |= (r[j] != pos && b.color[r[j]] == color && b.chain[r[j]] == label);
+                    }
+                    if (!already) gained++;
+                }
+            }
+            if (nown == 1) b.ls[label] += (gained << 16) - (1u << 16) + 1u;
+            else b.ls[label] = (gained << 16) | 1u;
+        }
+        k.sync();
+    } else {
+        bb_recount<N, NT>(b, k);
+    }
+    if (nown == 0 && prisoner == 1 && (b.ls[label] >> 16) == 1u) {       // :173-177
+        s.ko_move = s.moves;
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (b.color[q[i]] == EMPTY) s.ko_pos = q[i];
+    }
+    if (k.tid == 0) {
+        if (s.moves < G::MAXREC) { hist_hash[s.moves] = s.hash; hist_pos[s.moves] = (int16_t)pos; }
+        const unsigned bit = bloom_bit(s.hash);
+        b.bloom[bit >> 5] |= 1u << (bit & 31);
+    }
+    s.moves++;
+    k.sync();
+}
+
+// ---- selection (node.py:141-157 + pucb.py:8-29): one child per thread ---------------------------------------------
+template <int N, int NT>
+__device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const Tree& t, int node, bool cgos, Blk<NT>& k)
+{
+    constexpr int AP = Geo<N>::AP;
+    static_assert(sizeof(WAnalysis<N>) >= 3 * AP * 4, "child-row staging aliases the analysis scratch");
+    int* st_vis = reinterpret_cast<int*>(&sm.an);
+    int* st_vl = st_vis + AP;
+    float* st_vsum = reinterpret_cast<float*>(st_vl + AP);
+    double* st_pol = sm.s0;
+    const size_t row = (size_t)node * AP;
+    for (int c = k.tid; c < AP / 4; c += NT) {
+        cp_async16(st_vis + 4 * c, t.cvis + row + 4 * c);
+        cp_async16(st_vl + 4 * c, t.cvl + row + 4 * c);
+        cp_async16(st_vsum + 4 * c, t.cvsum + row + 4 * c);
+    }
+    for (int c = k.tid; c < AP / 2; c += NT) cp_async16(st_pol + 2 * c, t.cpol + row + 2 * c);
+    const int* h = t.hdr + (size_t)node * H_STRIDE;
+    const int nk = h[H_K];
+    const double sq = sqrt((double)(h[H_NV] + h[H_VL] + 1));
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    k.sync();
+    double bv = 0.0; int bi = 0x7fffffff;
+    for (int i = k.tid; i < nk; i += NT) {
+        const int cv = st_vis[i] + st_vl[i];
+        const double num = dmul(dmul(1.0, st_pol[i]), sq);
+        double v = num;
+        if (cv != 0) v = dadd(ddiv((double)st_vsum[i], (double)cv), ddiv(num, (double)(cv + 1)));
+        if (cgos && i == nk - 1) v = dsub(v, 0.1);
+        if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
+    }
+    return blk_argmax_d<N, NT>(sm, k, bv, bi);               // the barrier inside also protects the staging for the next use
+}
+
+// ---- expansion (tree.py:247-270 + node.py:41-72) ------------------------------------------------------------------
+template <int N, int NT>
+__device__ inline int expand_node_blk(BlkSmem<N, NT>& sm, const Dev& D, const Tree& t, int g, int* gs, const WBoard<N>& b, const BScal& s,
+                                      int color, const u64* hist_hash, unsigned move_key, Blk<NT>& k)
+{
+    using G = Geo<N>;
+    constexpr int CH = BlkSmem<N, NT>::CH, NW = NT / 32;
+    const int idx = gs[GS_NNODES];
+    if (idx >= D.tree.max_nodes) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_NODES; k.sync(); return -1; }
+    const size_t row = (size_t)idx * G::AP;
+    const bool superko = D.superko != 0;
+    // per-string liberty extremes and key XORs (wb_prepare_analysis, NT wide)
+    WAnalysis<N>& an = sm.an;
+    for (int c = k.tid; c < G::CP; c += NT) { an.lmin[c] = 0xffffu; an.lmax[c] = 0; an.cx[c] = 0; }
+    if (k.tid == 0) sm.nhit = 0;
+    k.sync();
+    {
+        const int other = opp(color);
+        for (int c = k.tid; c < G::CELLS; c += NT) {
+            const int col = b.color[c];
+            if (col == EMPTY) {
+                const int q[4] = { c - G::W, c - 1, c + 1, c + G::W };
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int cc = b.color[q[i]];
+                    if (cc == BLACK || cc == WHITE) { const int l = b.chain[q[i]]; atomicMin(&an.lmin[l], (unsigned)c); atomicMax(&an.lmax[l], (unsigned)c); }
+                }
+            } else if (superko && (col == BLACK || col == WHITE)) {
+                const int l = b.chain[c];
+                if ((b.ls[l] >> 16) == 1u) atomicXor(&an.cx[l], D.zob[other * G::CELLS + c]);
+            }
+        }
+    }
+    k.sync();
+    // lane-local status of every point; super-ko candidates whose hash hits the Bloom filter go to a hit list
+    u64* hit_h = reinterpret_cast<u64*>(sm.s0);
+    int16_t* hit_pt = reinterpret_cast<int16_t*>(sm.s1);
+    bool cand[CH];
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+        const int pi = c * NT + k.tid;
+        cand[c] = false;
+        if (pi < G::NN) {
+            const PointStatus st = wb_point_status<N>(b, an, s, onboard_pos<N>(pi), color, superko, D.zob, D.eye);
+            cand[c] = st.legal_pre && st.satari < 7 && !st.eye;                     // tree.py:261-263 (legality completed below)
+            sm.flag[pi] = 0;
+            if (cand[c] && st.need_scan) { const int hI = atomicAdd(&sm.nhit, 1); hit_h[hI] = st.h; hit_pt[hI] = (int16_t)pi; }
+        }
+    }
+    k.sync();
+    const int nh = sm.nhit;
+    if (nh > 0) {                                            // exact history scan (record.py:54-63), all (hit, entry) pairs in parallel
+        const int lim = (s.moves < G::MAXREC ? s.moves : G::MAXREC) - 1;             // live entries 1 .. lim
+        for (int j = k.tid; j < nh * lim; j += NT) {
+            const int hI = j / lim, e = 1 + (j - hI * lim);
+            if (hist_hash[e] == hit_h[hI]) sm.flag[hit_pt[hI]] = 1;
+        }
+        k.sync();
+    }
+    // ordered compaction of the candidates (raster order), PASS last (tree.py:264)
+    int total = 0;
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+        const int pi = c * NT + k.tid;
+        const bool ok = cand[c] && pi < G::NN && !sm.flag[pi];
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (k.lane == 0) sm.wcnt[k.warp] = __popc(m);
+        k.sync();
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) { const int v = sm.wcnt[w]; all += v; if (w < k.warp) before += v; }
+        if (ok) t.action[row + total + before + __popc(m & ((1u << k.lane) - 1))] = (int16_t)onboard_pos<N>(pi);
+        total += all;
+        k.sync();
+    }
+    const int nk = total + 1;
+    if (k.tid == 0) t.action[row + total] = PASS;
+    // get_tentative_policy (tree.py:509-519): Dirichlet(1,..,1) from the counter-based stream; the normaliser is summed
+    // in the warp shape of expand_node (lane l adds entries l, l+32, ... in order, then an xor butterfly)
+    const u64 gid = D.game_id[g];
+    for (int i = k.tid; i < nk; i += NT) sm.s0[i] = dsub(0.0, det_log(noise_u(D.seed, gid, move_key, (unsigned)idx, 0u, (unsigned)i)));
+    k.sync();
+    if (k.warp == 0) {
+        double part = 0.0;
+        for (int i = k.lane; i < nk; i += 32) part = dadd(part, sm.s0[i]);
+        const double sum = warp_shape_sum(part);
+        if (k.lane == 0) sm.bc_d = sum;
+    }
+    k.sync();
+    const double sum = sm.bc_d;
+    for (int i = k.tid; i < G::AP; i += NT) {
+        if (i < nk) t.cpol[row + i] = ddiv(sm.s0[i], sum); else { t.cpol[row + i] = 0.0; t.action[row + i] = 0; }
+        t.cidx[row + i] = NOT_EXPANDED; t.cval[row + i] = 0.0f; t.cvis[row + i] = 0; t.cvl[row + i] = 0; t.cvsum[row + i] = 0.0f;
+    }
+    if (k.tid < H_STRIDE) t.hdr[(size_t)idx * H_STRIDE + k.tid] = (k.tid == H_K) ? nk : 0;
+    if (k.tid == 0) gs[GS_NNODES] = idx + 1;
+    __threadfence_block();
+    k.sync();
+    return idx;
+}
+
+// ---- leaf queue (mcts/batch_data.py:18-27) ------------------------------------------------------------------------
+template <int N, int NT>
+__device__ inline void push_leaf_blk(BlkSmem<N, NT>& sm, const Dev& D, int g, int* gs, const WBoard<N>& b, const BScal& s, int color,
+                                     const unsigned* cur_path, int plen, int node_index, Blk<NT>& k)
+{
+    const int i = gs[GS_NLEAF];
+    if (i >= D.cap) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_QUEUE; k.sync(); return; }
+    const size_t q = (size_t)g * D.cap;
+    int dup_of = -1;
+    if (D.dedup) {                                           // identical path among the earlier entries of this batch
+        int first = 0x7fffffff;
+        for (int j = k.tid; j < i; j += NT) {
+            if (D.path_len[q + j] != plen) continue;
+            const unsigned* pj = D.path + (q + j) * D.max_depth;
+            bool same = true;
+            for (int d = plen - 1; d >= 0 && same; d--) same = (pj[d] == cur_path[d]);   // paths differ near the leaf first
+            if (same) { first = j; break; }
+        }
+        first = blk_min_i<N, NT>(sm, k, first);
+        if (first != 0x7fffffff) dup_of = first;
+    }
+    int nu = gs[GS_NUNIQ], slot;
+    if (dup_of >= 0) slot = D.leaf_slot[q + dup_of];
+    else {
+        slot = nu++;
+        uint8_t* dst = D.snap + (q + slot) * Snap<N>::BYTES;
+        using G = Geo<N>;
+        const int prev = (s.moves - 1 < G::MAXREC) ? D.hist_pos[(size_t)g * G::MAXREC + s.moves - 1] : 0;
+        if (k.tid == 0) {
+            const int pidx = (prev == PASS) ? -1 : ((prev % G::W) - 1) + ((prev / G::W) - 1) * N;
+            *reinterpret_cast<int16_t*>(dst) = (int16_t)pidx;
+            dst[2] = (s.moves > 1 && prev == PASS) ? 1 : 0;
+            dst[3] = (uint8_t)color;
+        }
+        for (int idx = k.tid; idx < G::NN; idx += NT) dst[Snap<N>::HDR + idx] = b.color[onboard_pos<N>(idx)];
+    }
+    k.sync();
+    if (k.tid == 0) {
+        D.path_len[q + i] = plen; D.leaf_node[q + i] = node_index; D.leaf_slot[q + i] = slot;
+        gs[GS_NLEAF] = i + 1; gs[GS_NUNIQ] = nu;
+    }
+    __threadfence_block();
+    k.sync();
+}
+
+// ---- up to `batch` descents of search_mcts for one game ----------------------------------------------------------
+template <int N, int NT>
+__global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, int visits, int batch, int strict)
+{
+    using G = Geo<N>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlkSmem<N, NT>& sm = *reinterpret_cast<BlkSmem<N, NT>*>(smem_raw);
+    Blk<NT> k;
+    const int g = blockIdx.x;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    const bool idle = !gs[GS_ACTIVE] || gs[GS_FINISHED] || gs[GS_ERROR] || gs[GS_DONE];
+    k.sync();
+    if (k.tid == 0) { gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+    __threadfence_block();
+    k.sync();
+    if (idle) return;
+    BScal rs;
+    bb_load<N, NT>(sm.root, rs, pool_of<N>(D), g, k);
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    const int root_color = gs[GS_COLOR];
+    u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
+    int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
+    const unsigned move_key = (unsigned)rs.moves;
+    const bool prof = D.prof && g == 0 && k.tid == 0;
+    for (int bi = 0; bi < batch; bi++) {
+        const int desc = gs[GS_DESC];
+        if (desc >= visits) { k.sync(); if (k.tid == 0) gs[GS_DONE] = 1; break; }
+        if (desc > 0) {                                      // is_move_decided (time_manager.py:146-163)
+            const int nk = t.hdr[H_K];
+            int top1 = 0;
+            for (int i = k.tid; i < nk; i += NT) top1 = max(top1, t.cvis[i]);
+            top1 = blk_max_i<N, NT>(sm, k, top1);
+            int nmax = 0, top2 = 0;
+            for (int i = k.tid; i < nk; i += NT) { const int v = t.cvis[i]; if (v == top1) nmax++; else top2 = max(top2, v); }
+            blk_sum_max<N, NT>(sm, k, nmax, top2);
+            if (nmax >= 2) top2 = top1;
+            const int remaining = visits - t.hdr[H_NV];
+            const int cutoff = strict ? 0 : top1 - top2;
+            if (remaining < cutoff) { k.sync(); if (k.tid == 0) gs[GS_DONE] = 1; break; }
+        }
+        long long pt0 = prof ? clock64() : 0;
+        bb_copy<N, NT>(sm.scratch, sm.root, k);              // tree.py:147
+        if (prof) { const long long c = clock64(); D.prof[0] += c - pt0; pt0 = c; }
+        BScal s = rs;
+        int color = root_color, cur = 0, plen = 0;
+        unsigned* path = D.path + ((size_t)g * D.cap + gs[GS_NLEAF]) * D.max_depth;
+        bool fail = false;
+        for (;;) {
+            const int next = select_puct_blk<N, NT>(sm, t, cur, D.cgos != 0, k);     // :213
+            if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
+            const size_t row = (size_t)cur * G::AP;
+            const int mv = t.action[row + next];
+            if (k.tid == 0) path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+            plen++;
+            bb_put_stone<N, NT>(sm, sm.scratch, s, mv, color, D.zob, hh, hp, k);      // :217
+            if (prof) { const long long c = clock64(); D.prof[2] += c - pt0; pt0 = c; }
+            color = opp(color);
+            const int cv_before = t.cvis[row + next] + t.cvl[row + next];
+            int ci = t.cidx[row + next];
+            k.sync();                                        // all threads have read the edge before thread 0 changes it
+            if (k.tid == 0) { t.hdr[(size_t)cur * H_STRIDE + H_VL] += 1; t.cvl[row + next] += 1; }      // :221
+            int expand_threshold = 1;
+            if (s.moves > 2) {                               // :224-229
+                if (s.moves - 1 >= G::MAXREC) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_HISTORY; fail = true; break; }
+                if (hp[s.moves - 1] == PASS && hp[s.moves - 2] == PASS) expand_threshold = 10000000;
+            }
+            if (cv_before + 1 < expand_threshold + 1) {      // :231-241 (children_visits + children_virtual_loss after add_virtual_loss)
+                if (ci == NOT_EXPANDED) {
+                    if (prof) pt0 = clock64();
+                    ci = expand_node_blk<N, NT>(sm, D, t, g, gs, sm.scratch, s, color, hh, move_key, k);
+                    if (prof) { const long long c = clock64(); D.prof[3] += c - pt0; pt0 = c; D.prof[6]++; }
+                    if (ci < 0) { fail = true; break; }
+                    if (k.tid == 0) t.cidx[row + next] = ci;
+                }
+                if (prof) pt0 = clock64();
+                push_leaf_blk<N, NT>(sm, D, g, gs, sm.scratch, s, color, path, plen, ci, k);
+                if (prof) { const long long c = clock64(); D.prof[4] += c - pt0; pt0 = c; D.prof[7]++; }
+                break;
+            }
+            cur = ci;
+            if (plen >= D.max_depth) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_DEPTH; fail = true; break; }
+            __threadfence_block();
+            k.sync();                                        // the virtual-loss update is visible to the next selection
+        }
+        __threadfence_block();
+        k.sync();
+        if (fail) break;
+        if (k.tid == 0) gs[GS_DESC] = desc + 1;
+        __threadfence_block();
+        k.sync();
+    }
+}
+
+// ---- process_mini_batch after the forward pass (tree.py:287-315) ----------------------------------------------------
+template <int N, int NT>
+__global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    const int nl = gs[GS_NLEAF];
+    if (nl == 0) return;
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    const int slot0 = gs[GS_SLOT0];
+    const size_t q = (size_t)g * D.cap;
+    __shared__ int bad;
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    // (a) priors and raw value of every evaluated node: independent of each other, one warp per leaf (node.py:86-93)
+    for (int i = warp; i < nl; i += NT / 32) {
+        const int slot = slot0 + D.leaf_slot[q + i];
+        if (slot >= D.slot_cap) { if (lane == 0) bad = 1; continue; }
+        const int ni = D.leaf_node[q + i];
+        if (ni < 0) continue;
+        const float* pol = D.policy + (size_t)slot * G::A;
+        const float* v = D.value + (size_t)slot * 3;
+        const size_t row = (size_t)ni * G::AP;
+        const int nk = t.hdr[(size_t)ni * H_STRIDE + H_K];
+        for (int c = lane; c < nk; c += 32) {
+            const int a = t.action[row + c];
+            float p;
+            if (a == PASS) { p = pol[G::NN]; if (use_logit) p = __fsub_rn(p, 0.5f); }
+            else p = pol[(a / G::W - 1) * N + (a % G::W - 1)];
+            t.cpol[row + c] = (double)p;
+        }
+        if (lane == 0) t.hdr[(size_t)ni * H_STRIDE + H_RAW] = __float_as_int(__fadd_rn(__fmul_rn(v[1], 0.5f), v[2]));
+    }
+    __syncthreads();
+    if (bad) { if (tid == 0) gs[GS_ERROR] |= ERR_QUEUE; return; }
+    if (warp != 0) return;
+    // (b) values walk the paths back to the root, leaf by leaf in queue order (fp32 sums depend on it)
+    for (int i = 0; i < nl; i++) {
+        const int slot = slot0 + D.leaf_slot[q + i];
+        const float* v = D.value + (size_t)slot * 3;
+        const float v0 = v[0], v1 = v[1];
+        const int plen = D.path_len[q + i];
+        if (plen > 0) {
+            const unsigned* path = D.path + (q + i) * D.max_depth;
+            const float val0 = __fadd_rn(v0, __fmul_rn(v1, 0.5f));
+            const float val1 = __fsub_rn(1.0f, val0), val2 = __fsub_rn(1.0f, val1);
+            for (int d0 = 0; d0 < plen; d0 += 32) {
+                const int d = d0 + lane;
+                if (d < plen) {
+                    const unsigned e = path[plen - 1 - d];
+                    const int node = (int)(e >> PATH_NODE_SHIFT), c = (int)(e & ((1u << PATH_NODE_SHIFT) - 1));
+                    const float val = d == 0 ? val0 : ((d & 1) ? val1 : val2);
+                    const size_t row = (size_t)node * G::AP;
+                    if (d == 0) t.cval[row + c] = val0;
+                    t.cvsum[row + c] = __fadd_rn(t.cvsum[row + c], val);
+                    t.cvis[row + c] += 1; t.cvl[row + c] -= 1;
+                    int* h = t.hdr + (size_t)node * H_STRIDE;
+                    h[H_VSUM] = __float_as_int(__fadd_rn(__int_as_float(h[H_VSUM]), val));
+                    h[H_NV] += 1; h[H_VL] -= 1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { gs[GS_EVALS] += nl; gs[GS_UEVALS] += gs[GS_NUNIQ]; }
+}
+
+}  // namespace tg

@@ -4,6 +4,7 @@
 // packs the DualNet parameters, and queues the kernel sequence of one move of every game on one CUDA stream.
 #include "../../include/tamago_b200.h"
 #include "tg_search.cuh"
+#include "tg_block.cuh"
 #include "tg_dualnet.cuh"
 
 #include <cmath>
@@ -67,6 +68,7 @@ struct tg_engine {
     float last_ms = 0.f, last_eval_ms = 0.f;
     int64_t last_eval_slots = 0;
     int sms = 148;
+    bool puct_warp = false;
 };
 
 template <class T> static int dalloc(tg_engine* e, T** p, size_t n, bool zero = true)
@@ -144,6 +146,13 @@ template <int BN> static int setup_kernel_attrs()
     CK(cudaFuncSetAttribute(k_root_begin<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_descend_sh<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    return 0;
+}
+constexpr int PUCT_NT = 256;              // threads per game in the block-per-game PUCT kernels: 1024 games = one wave of 8 CTAs per SM
+template <int BN> static int setup_blk_attr()
+{
+    static_assert(sizeof(BlkSmem<BN, PUCT_NT>) <= 48 * 1024, "block-per-game scratch fits the default shared-memory window");
+    CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, PUCT_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return 0;
 }
 template <int BN, int G> static int setup_tc_attr()
@@ -294,6 +303,9 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     if (rc) return bail(rc);
     DISPATCH_N(e, (rc = setup_tc_attr<BN, TcGroup<BN>::G>()));
     if (rc) return bail(rc);
+    DISPATCH_N(e, rc = setup_blk_attr<BN>());
+    if (rc) return bail(rc);
+    e->puct_warp = getenv("TG_PUCT_WARP") != nullptr;
 
     // default Zobrist table (splitmix64 stream); tg_set_zobrist replaces it
     {
@@ -633,11 +645,16 @@ extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int3
                 const int batch = e->cfg.batch_size;
                 const int iters = (visits + batch - 1) / batch + 1;
                 for (int it = 0; it < iters && !rc; it++) {
-                    k_descend_puct<BN><<<grid, thr, sm, e->stream>>>(D, visits, batch, strict);
-                    e->launches++;
-                    rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
-                    k_backup<BN><<<grid, thr, 0, e->stream>>>(D, 0);
-                    e->launches++;
+                    if (e->puct_warp) {                  // warp-per-game kernels (TG_PUCT_WARP=1: A/B measurements)
+                        k_descend_puct<BN><<<grid, thr, sm, e->stream>>>(D, visits, batch, strict);
+                        rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
+                        k_backup<BN><<<grid, thr, 0, e->stream>>>(D, 0);
+                    } else {                             // block-per-game: a ply runs PUCT_NT threads wide (tg_block.cuh)
+                        k_descend_puct_blk<BN, PUCT_NT><<<games, PUCT_NT, sizeof(BlkSmem<BN, PUCT_NT>), e->stream>>>(D, visits, batch, strict);
+                        rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
+                        k_backup_blk<BN, PUCT_NT><<<games, PUCT_NT, 0, e->stream>>>(D, 0);
+                    }
+                    e->launches += 2;
                 }
             }
             if (!rc) {
