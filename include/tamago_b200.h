@@ -84,6 +84,7 @@ typedef struct tg_ply_dump {
     uint8_t*  cand;     /* [games][plies][2][N*N]   expansion candidates (mcts/tree.py:260-263)  */
     int32_t*  score;    /* [games][plies]           count_score (go_board.py:561)                */
     int32_t   plies;    /* plies allocated per game */
+    int32_t*  tt_score; /* [games][plies]           Tromp-Taylor area score, Black - White (tg_config.scoring = 1); may be NULL */
 } tg_ply_dump;
 
 /* Result of one move of every game (host buffers, caller-owned; any pointer may be NULL). */

@@ -30,7 +30,7 @@ class Weights(C.Structure):
 
 class PlyDump(C.Structure):
     _fields_ = [("color", u8p), ("libs", i16p), ("size", i16p), ("scal", i32p), ("hash", u64p), ("legal", u8p),
-                ("satari", i16p), ("eye", u8p), ("cand", u8p), ("score", i32p), ("plies", C.c_int32)]
+                ("satari", i16p), ("eye", u8p), ("cand", u8p), ("score", i32p), ("plies", C.c_int32), ("tt_score", i32p)]
 
 
 class StepResult(C.Structure):

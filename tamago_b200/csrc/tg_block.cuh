@@ -24,10 +24,19 @@ template <int N, int NT> struct BlkSmem {
     using G = Geo<N>;
     static constexpr int NW = NT / 32;
     static constexpr int CH = (G::NN + NT - 1) / NT;      // analysis points per thread
+    // child rows of a node staged from the HBM/L2 node pool; two buffers: the rows of the node a descent moves to are
+    // fetched (cp.async) while put_stone runs, the root's rows for the next descent while the leaf is expanded
+    struct NodeStage {
+        alignas(16) double pol[G::AP];
+        alignas(16) int vis[G::AP]; int vl[G::AP]; float vsum[G::AP]; int cidx[G::AP];
+        alignas(16) int16_t action[G::AP];
+        alignas(16) int hdr[H_STRIDE];
+    } st[2];
+    alignas(16) uint32_t eye2[4096];                       // eye table, two bits per 3x3 code (pattern.py:53-98)
     WBoard<N> root;
     WBoard<N> scratch;
-    alignas(16) WAnalysis<N> an;                           // expansion scratch; selection stages child rows here
-    alignas(16) double s0[G::AP];                          // selection: priors; expansion: super-ko hit hashes, then -log u
+    alignas(16) WAnalysis<N> an;                           // expansion scratch
+    alignas(16) double s0[G::AP];                          // expansion: super-ko hit hashes, then -log u
     double s1[G::AP];                                      // expansion: points of the super-ko hits (int16)
     // reductions (ping-pong: one barrier per reduction)
     u64 r_x[2][NW]; int r_i[2][NW]; int r_j[2][NW]; double r_d[2][NW];
@@ -163,7 +172,9 @@ template <int N, int NT> __device__ inline void bb_copy(WBoard<N>& dst, const WB
     k.sync();
 }
 
-// GoBoard.put_stone (go_board.py:131-185); same steps as wb_put_stone, sweeps NT wide
+// GoBoard.put_stone (go_board.py:131-185); same steps as wb_put_stone, sweeps NT wide.  The common case (nothing
+// captured, at most one own string extended) costs two barriers: every thread reads the neighbourhood, thread 0 applies
+// the move (stone, label, local liberty update, history, Bloom bit), every thread re-reads what the ko rule needs.
 template <int N, int NT>
 __device__ inline void bb_put_stone(BlkSmem<N, NT>& sm, WBoard<N>& b, BScal& s, int pos, int color, const u64* __restrict__ zob,
                                     u64* hist_hash, int16_t* hist_pos, Blk<NT>& k)
@@ -172,6 +183,7 @@ __device__ inline void bb_put_stone(BlkSmem<N, NT>& sm, WBoard<N>& b, BScal& s, 
     if (pos == PASS) {                                       // :138-141
         if (k.tid == 0 && s.moves < G::MAXREC) { hist_hash[s.moves] = s.hash; hist_pos[s.moves] = 0; }
         s.moves++;
+        __threadfence_block();
         k.sync();
         return;
     }
@@ -194,35 +206,13 @@ __device__ inline void bb_put_stone(BlkSmem<N, NT>& sm, WBoard<N>& b, BScal& s, 
         }
     }
     const int label = nown > 0 ? own[0] : pos;
-    k.sync();                                                // every thread has read the neighbourhood
-    if (k.tid == 0) { b.color[pos] = (uint8_t)color; b.chain[pos] = (uint16_t)label; }
     s.hash ^= zob[color * G::CELLS + pos];
+    k.sync();                                                // every thread has read the neighbourhood
     int prisoner = 0;
-    if (ncap > 0 || nown > 1) {
-        u64 hx = 0; int cnt = 0;
-        for (int c = k.tid; c < G::CELLS; c += NT) {
-            const int cc = b.color[c];
-            if (cc == other) {
-                const int l = b.chain[c];
-                bool hit = false;
-                for (int j = 0; j < ncap; j++) hit |= (cap[j] == l);
-                if (hit) { b.color[c] = EMPTY; hx ^= zob[other * G::CELLS + c]; cnt++; }
-            } else if (cc == color && c != pos) {
-                const int l = b.chain[c];
-                bool hit = false;
-                for (int j = 1; j < nown; j++) hit |= (own[j] == l);
-                if (hit) b.chain[c] = (uint16_t)label;
-            }
-        }
-        blk_xor_sum<N, NT>(sm, k, hx, cnt);                  // (contains a barrier)
-        s.hash ^= hx;
-        prisoner = cnt;
-    }
-    if (color == BLACK) s.pris0 += prisoner; else s.pris1 += prisoner;
-    k.sync();
     if (ncap == 0 && nown <= 1) {
-        if (k.tid == 0) {                                    // local liberty update, see wb_put_stone
-            int el[4], ne = 0;
+        if (k.tid == 0) {
+            b.color[pos] = (uint8_t)color; b.chain[pos] = (uint16_t)label;
+            int el[4], ne = 0;                               // local liberty update, see wb_put_stone
             unsigned gained = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -245,11 +235,38 @@ __device__ inline void bb_put_stone(BlkSmem<N, NT>& sm, WBoard<N>& b, BScal& s, 
             }
             if (nown == 1) b.ls[label] += (gained << 16) - (1u << 16) + 1u;
             else b.ls[label] = (gained << 16) | 1u;
+            if (s.moves < G::MAXREC) { hist_hash[s.moves] = s.hash; hist_pos[s.moves] = (int16_t)pos; }
+            const unsigned bit = bloom_bit(s.hash);
+            b.bloom[bit >> 5] |= 1u << (bit & 31);
+            __threadfence_block();
         }
         k.sync();
-    } else {
-        bb_recount<N, NT>(b, k);
+        s.moves++;
+        return;                                              // no prisoners: the ko rule (:173-177) cannot apply
     }
+    if (k.tid == 0) { b.color[pos] = (uint8_t)color; b.chain[pos] = (uint16_t)label; }
+    {
+        u64 hx = 0; int cnt = 0;
+        for (int c = k.tid; c < G::CELLS; c += NT) {
+            const int cc = b.color[c];
+            if (cc == other) {
+                const int l = b.chain[c];
+                bool hit = false;
+                for (int j = 0; j < ncap; j++) hit |= (cap[j] == l);
+                if (hit) { b.color[c] = EMPTY; hx ^= zob[other * G::CELLS + c]; cnt++; }
+            } else if (cc == color && c != pos) {
+                const int l = b.chain[c];
+                bool hit = false;
+                for (int j = 1; j < nown; j++) hit |= (own[j] == l);
+                if (hit) b.chain[c] = (uint16_t)label;
+            }
+        }
+        blk_xor_sum<N, NT>(sm, k, hx, cnt);                  // (contains a barrier)
+        s.hash ^= hx;
+        prisoner = cnt;
+    }
+    if (color == BLACK) s.pris0 += prisoner; else s.pris1 += prisoner;
+    bb_recount<N, NT>(b, k);                                 // its first barrier orders the sweep above before the recount
     if (nown == 0 && prisoner == 1 && (b.ls[label] >> 16) == 1u) {       // :173-177
         s.ko_move = s.moves;
 #pragma unroll
@@ -259,43 +276,46 @@ __device__ inline void bb_put_stone(BlkSmem<N, NT>& sm, WBoard<N>& b, BScal& s, 
         if (s.moves < G::MAXREC) { hist_hash[s.moves] = s.hash; hist_pos[s.moves] = (int16_t)pos; }
         const unsigned bit = bloom_bit(s.hash);
         b.bloom[bit >> 5] |= 1u << (bit & 31);
+        __threadfence_block();
     }
     s.moves++;
     k.sync();
 }
 
-// ---- selection (node.py:141-157 + pucb.py:8-29): one child per thread ---------------------------------------------
+// ---- node staging: one burst of 16-byte asynchronous copies per node ---------------------------------------------------
 template <int N, int NT>
-__device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const Tree& t, int node, bool cgos, Blk<NT>& k)
+__device__ __forceinline__ void stage_node(typename BlkSmem<N, NT>::NodeStage& st, const Tree& t, int node, const Blk<NT>& k)
 {
     constexpr int AP = Geo<N>::AP;
-    static_assert(sizeof(WAnalysis<N>) >= 3 * AP * 4, "child-row staging aliases the analysis scratch");
-    int* st_vis = reinterpret_cast<int*>(&sm.an);
-    int* st_vl = st_vis + AP;
-    float* st_vsum = reinterpret_cast<float*>(st_vl + AP);
-    double* st_pol = sm.s0;
     const size_t row = (size_t)node * AP;
     for (int c = k.tid; c < AP / 4; c += NT) {
-        cp_async16(st_vis + 4 * c, t.cvis + row + 4 * c);
-        cp_async16(st_vl + 4 * c, t.cvl + row + 4 * c);
-        cp_async16(st_vsum + 4 * c, t.cvsum + row + 4 * c);
+        cp_async16(st.vis + 4 * c, t.cvis + row + 4 * c);
+        cp_async16(st.vl + 4 * c, t.cvl + row + 4 * c);
+        cp_async16(st.vsum + 4 * c, t.cvsum + row + 4 * c);
+        cp_async16(st.cidx + 4 * c, t.cidx + row + 4 * c);
     }
-    for (int c = k.tid; c < AP / 2; c += NT) cp_async16(st_pol + 2 * c, t.cpol + row + 2 * c);
-    const int* h = t.hdr + (size_t)node * H_STRIDE;
-    const int nk = h[H_K];
-    const double sq = sqrt((double)(h[H_NV] + h[H_VL] + 1));
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    k.sync();
+    for (int c = k.tid; c < AP / 2; c += NT) cp_async16(st.pol + 2 * c, t.cpol + row + 2 * c);
+    for (int c = k.tid; c < AP / 8; c += NT) cp_async16(st.action + 8 * c, t.action + row + 8 * c);
+    if (k.tid < H_STRIDE / 4) cp_async16(st.hdr + 4 * k.tid, t.hdr + (size_t)node * H_STRIDE + 4 * k.tid);
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---- selection (node.py:141-157 + pucb.py:8-29) on a staged node: one child per thread -----------------------------------
+template <int N, int NT>
+__device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const typename BlkSmem<N, NT>::NodeStage& st, bool cgos, Blk<NT>& k)
+{
+    const int nk = st.hdr[H_K];
+    const double sq = sqrt((double)(st.hdr[H_NV] + st.hdr[H_VL] + 1));
     double bv = 0.0; int bi = 0x7fffffff;
     for (int i = k.tid; i < nk; i += NT) {
-        const int cv = st_vis[i] + st_vl[i];
-        const double num = dmul(dmul(1.0, st_pol[i]), sq);
+        const int cv = st.vis[i] + st.vl[i];
+        const double num = dmul(dmul(1.0, st.pol[i]), sq);
         double v = num;
-        if (cv != 0) v = dadd(ddiv((double)st_vsum[i], (double)cv), ddiv(num, (double)(cv + 1)));
+        if (cv != 0) v = dadd(ddiv((double)st.vsum[i], (double)cv), ddiv(num, (double)(cv + 1)));
         if (cgos && i == nk - 1) v = dsub(v, 0.1);
         if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
     }
-    return blk_argmax_d<N, NT>(sm, k, bv, bi);               // the barrier inside also protects the staging for the next use
+    return blk_argmax_d<N, NT>(sm, k, bv, bi);
 }
 
 // ---- expansion (tree.py:247-270 + node.py:41-72) ------------------------------------------------------------------
@@ -341,7 +361,7 @@ __device__ inline int expand_node_blk(BlkSmem<N, NT>& sm, const Dev& D, const Tr
         const int pi = c * NT + k.tid;
         cand[c] = false;
         if (pi < G::NN) {
-            const PointStatus st = wb_point_status<N>(b, an, s, onboard_pos<N>(pi), color, superko, D.zob, D.eye);
+            const PointStatus st = wb_point_status<N>(b, an, s, onboard_pos<N>(pi), color, superko, D.zob, EyeLutPacked{sm.eye2});
             cand[c] = st.legal_pre && st.satari < 7 && !st.eye;                     // tree.py:261-263 (legality completed below)
             sm.flag[pi] = 0;
             if (cand[c] && st.need_scan) { const int hI = atomicAdd(&sm.nhit, 1); hit_h[hI] = st.h; hit_pt[hI] = (int16_t)pi; }
@@ -446,7 +466,7 @@ __device__ inline void push_leaf_blk(BlkSmem<N, NT>& sm, const Dev& D, int g, in
 
 // ---- up to `batch` descents of search_mcts for one game ----------------------------------------------------------
 template <int N, int NT>
-__global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, int visits, int batch, int strict)
+__global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, const uint32_t* __restrict__ eye2, int visits, int batch, int strict)
 {
     using G = Geo<N>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -460,9 +480,11 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, int visits, int 
     __threadfence_block();
     k.sync();
     if (idle) return;
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    stage_node<N, NT>(sm.st[0], t, 0, k);                    // the root's rows arrive while the board is loaded
+    for (int i = k.tid; i < 4096 / 4; i += NT) reinterpret_cast<uint4*>(sm.eye2)[i] = reinterpret_cast<const uint4*>(eye2)[i];
     BScal rs;
     bb_load<N, NT>(sm.root, rs, pool_of<N>(D), g, k);
-    const Tree t = tree_of<G::AP>(D.tree, g);
     const int root_color = gs[GS_COLOR];
     u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
     int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
@@ -471,16 +493,18 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, int visits, int 
     for (int bi = 0; bi < batch; bi++) {
         const int desc = gs[GS_DESC];
         if (desc >= visits) { k.sync(); if (k.tid == 0) gs[GS_DONE] = 1; break; }
+        stage_wait();
+        k.sync();                                            // root rows (buffer 0) are in shared memory
         if (desc > 0) {                                      // is_move_decided (time_manager.py:146-163)
-            const int nk = t.hdr[H_K];
+            const int nk = sm.st[0].hdr[H_K];
             int top1 = 0;
-            for (int i = k.tid; i < nk; i += NT) top1 = max(top1, t.cvis[i]);
+            for (int i = k.tid; i < nk; i += NT) top1 = max(top1, sm.st[0].vis[i]);
             top1 = blk_max_i<N, NT>(sm, k, top1);
             int nmax = 0, top2 = 0;
-            for (int i = k.tid; i < nk; i += NT) { const int v = t.cvis[i]; if (v == top1) nmax++; else top2 = max(top2, v); }
+            for (int i = k.tid; i < nk; i += NT) { const int v = sm.st[0].vis[i]; if (v == top1) nmax++; else top2 = max(top2, v); }
             blk_sum_max<N, NT>(sm, k, nmax, top2);
             if (nmax >= 2) top2 = top1;
-            const int remaining = visits - t.hdr[H_NV];
+            const int remaining = visits - sm.st[0].hdr[H_NV];
             const int cutoff = strict ? 0 : top1 - top2;
             if (remaining < cutoff) { k.sync(); if (k.tid == 0) gs[GS_DONE] = 1; break; }
         }
@@ -488,45 +512,57 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, int visits, int 
         bb_copy<N, NT>(sm.scratch, sm.root, k);              // tree.py:147
         if (prof) { const long long c = clock64(); D.prof[0] += c - pt0; pt0 = c; }
         BScal s = rs;
-        int color = root_color, cur = 0, plen = 0;
+        int color = root_color, cur = 0, plen = 0, buf = 0;
         unsigned* path = D.path + ((size_t)g * D.cap + gs[GS_NLEAF]) * D.max_depth;
         bool fail = false;
         for (;;) {
-            const int next = select_puct_blk<N, NT>(sm, t, cur, D.cgos != 0, k);     // :213
+            const typename BlkSmem<N, NT>::NodeStage& st = sm.st[buf];
+            const int next = select_puct_blk<N, NT>(sm, st, D.cgos != 0, k);         // :213
             if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
             const size_t row = (size_t)cur * G::AP;
-            const int mv = t.action[row + next];
-            if (k.tid == 0) path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+            const int mv = st.action[next];
+            const int cv_before = st.vis[next] + st.vl[next];
+            int ci = st.cidx[next];
+            // the child's rows are needed next unless this edge ends the descent: fetch them under put_stone
+            const bool spec = ci != NOT_EXPANDED && cv_before >= 1;
+            if (spec) stage_node<N, NT>(sm.st[buf ^ 1], t, ci, k);
+            if (k.tid == 0) {
+                path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+                t.hdr[(size_t)cur * H_STRIDE + H_VL] = st.hdr[H_VL] + 1; t.cvl[row + next] = st.vl[next] + 1;    // :221 add_virtual_loss
+            }
             plen++;
             bb_put_stone<N, NT>(sm, sm.scratch, s, mv, color, D.zob, hh, hp, k);      // :217
             if (prof) { const long long c = clock64(); D.prof[2] += c - pt0; pt0 = c; }
             color = opp(color);
-            const int cv_before = t.cvis[row + next] + t.cvl[row + next];
-            int ci = t.cidx[row + next];
-            k.sync();                                        // all threads have read the edge before thread 0 changes it
-            if (k.tid == 0) { t.hdr[(size_t)cur * H_STRIDE + H_VL] += 1; t.cvl[row + next] += 1; }      // :221
             int expand_threshold = 1;
             if (s.moves > 2) {                               // :224-229
                 if (s.moves - 1 >= G::MAXREC) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_HISTORY; fail = true; break; }
                 if (hp[s.moves - 1] == PASS && hp[s.moves - 2] == PASS) expand_threshold = 10000000;
             }
             if (cv_before + 1 < expand_threshold + 1) {      // :231-241 (children_visits + children_virtual_loss after add_virtual_loss)
+                if (spec) stage_wait();                      // (two-pass rule ended the descent: drain the unused fetch)
+                k.sync();
+                // root rows for the next descent are fetched under the expansion -- unless the expansion changes the root's
+                // own child-index row (a depth-1 leaf): then the fetch has to follow that write
+                const bool root_edge = cur == 0 && ci == NOT_EXPANDED;
+                if (!root_edge) stage_node<N, NT>(sm.st[0], t, 0, k);
                 if (ci == NOT_EXPANDED) {
                     if (prof) pt0 = clock64();
                     ci = expand_node_blk<N, NT>(sm, D, t, g, gs, sm.scratch, s, color, hh, move_key, k);
                     if (prof) { const long long c = clock64(); D.prof[3] += c - pt0; pt0 = c; D.prof[6]++; }
                     if (ci < 0) { fail = true; break; }
-                    if (k.tid == 0) t.cidx[row + next] = ci;
+                    if (k.tid == 0) { t.cidx[row + next] = ci; __threadfence_block(); }
+                    if (root_edge) { k.sync(); stage_node<N, NT>(sm.st[0], t, 0, k); }
                 }
                 if (prof) pt0 = clock64();
                 push_leaf_blk<N, NT>(sm, D, g, gs, sm.scratch, s, color, path, plen, ci, k);
                 if (prof) { const long long c = clock64(); D.prof[4] += c - pt0; pt0 = c; D.prof[7]++; }
                 break;
             }
-            cur = ci;
+            cur = ci; buf ^= 1;
             if (plen >= D.max_depth) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_DEPTH; fail = true; break; }
-            __threadfence_block();
-            k.sync();                                        // the virtual-loss update is visible to the next selection
+            stage_wait();
+            k.sync();                                        // the child's rows are in shared memory
         }
         __threadfence_block();
         k.sync();
@@ -535,9 +571,13 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, int visits, int 
         __threadfence_block();
         k.sync();
     }
+    stage_wait();
 }
 
 // ---- process_mini_batch after the forward pass (tree.py:287-315) ----------------------------------------------------
+// (a) priors / raw value of every evaluated node: all (leaf, child) pairs are independent and are spread over the
+//     whole block with several loads in flight per thread; (b) values: one warp walks the leaves in queue order (fp32
+//     sums depend on it) with the next leaf's path entries already in flight.
 template <int N, int NT>
 __global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit)
 {
@@ -552,46 +592,69 @@ __global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit)
     __shared__ int bad;
     if (tid == 0) bad = 0;
     __syncthreads();
-    // (a) priors and raw value of every evaluated node: independent of each other, one warp per leaf (node.py:86-93)
-    for (int i = warp; i < nl; i += NT / 32) {
+    for (int i = tid; i < nl; i += NT) {
         const int slot = slot0 + D.leaf_slot[q + i];
-        if (slot >= D.slot_cap) { if (lane == 0) bad = 1; continue; }
+        if (slot >= D.slot_cap) { bad = 1; continue; }
         const int ni = D.leaf_node[q + i];
-        if (ni < 0) continue;
-        const float* pol = D.policy + (size_t)slot * G::A;
-        const float* v = D.value + (size_t)slot * 3;
-        const size_t row = (size_t)ni * G::AP;
-        const int nk = t.hdr[(size_t)ni * H_STRIDE + H_K];
-        for (int c = lane; c < nk; c += 32) {
-            const int a = t.action[row + c];
-            float p;
-            if (a == PASS) { p = pol[G::NN]; if (use_logit) p = __fsub_rn(p, 0.5f); }
-            else p = pol[(a / G::W - 1) * N + (a % G::W - 1)];
-            t.cpol[row + c] = (double)p;
+        if (ni >= 0) {
+            const float* v = D.value + (size_t)slot * 3;
+            t.hdr[(size_t)ni * H_STRIDE + H_RAW] = __float_as_int(__fadd_rn(__fmul_rn(v[1], 0.5f), v[2]));           // tree.py:300
         }
-        if (lane == 0) t.hdr[(size_t)ni * H_STRIDE + H_RAW] = __float_as_int(__fadd_rn(__fmul_rn(v[1], 0.5f), v[2]));
     }
     __syncthreads();
     if (bad) { if (tid == 0) gs[GS_ERROR] |= ERR_QUEUE; return; }
+    constexpr int U = 4;
+    for (int p0 = tid; p0 < nl * G::AP; p0 += NT * U) {                          // node.py:86-93, tree.py:287-299
+        int ni[U], c[U], a[U]; const float* pol[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int p = p0 + u * NT;
+            const int i = p / G::AP;
+            c[u] = p - i * G::AP; ni[u] = -1; a[u] = 0; pol[u] = nullptr;
+            if (p < nl * G::AP) {
+                ni[u] = D.leaf_node[q + i];
+                pol[u] = D.policy + (size_t)(slot0 + D.leaf_slot[q + i]) * G::A;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (ni[u] >= 0) { if (c[u] < t.hdr[(size_t)ni[u] * H_STRIDE + H_K]) a[u] = t.action[(size_t)ni[u] * G::AP + c[u]]; else ni[u] = -1; }
+        float pv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (ni[u] >= 0) pv[u] = a[u] == PASS ? pol[u][G::NN] : pol[u][(a[u] / G::W - 1) * N + (a[u] % G::W - 1)];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (ni[u] >= 0) {
+                float p = pv[u];
+                if (a[u] == PASS && use_logit) p = __fsub_rn(p, 0.5f);                                                // tree.py:292-294
+                t.cpol[(size_t)ni[u] * G::AP + c[u]] = (double)p;
+            }
+    }
     if (warp != 0) return;
-    // (b) values walk the paths back to the root, leaf by leaf in queue order (fp32 sums depend on it)
+    // (b) tree.py:301-313 + node.py:118-138
+    auto leaf_head = [&](int i, float& val0, int& plen, unsigned& e0) {
+        const float* v = D.value + (size_t)(slot0 + D.leaf_slot[q + i]) * 3;
+        val0 = __fadd_rn(v[0], __fmul_rn(v[1], 0.5f));                                                                // :303
+        plen = D.path_len[q + i];
+        e0 = lane < plen ? D.path[(q + i) * D.max_depth + plen - 1 - lane] : 0u;
+    };
+    float val0n = 0.f; int plenn = 0; unsigned en = 0;
+    leaf_head(0, val0n, plenn, en);
     for (int i = 0; i < nl; i++) {
-        const int slot = slot0 + D.leaf_slot[q + i];
-        const float* v = D.value + (size_t)slot * 3;
-        const float v0 = v[0], v1 = v[1];
-        const int plen = D.path_len[q + i];
+        const float val0 = val0n; const int plen = plenn; const unsigned e0 = en;
+        if (i + 1 < nl) leaf_head(i + 1, val0n, plenn, en);                      // next leaf's loads overlap this leaf's updates
         if (plen > 0) {
             const unsigned* path = D.path + (q + i) * D.max_depth;
-            const float val0 = __fadd_rn(v0, __fmul_rn(v1, 0.5f));
             const float val1 = __fsub_rn(1.0f, val0), val2 = __fsub_rn(1.0f, val1);
             for (int d0 = 0; d0 < plen; d0 += 32) {
-                const int d = d0 + lane;
+                const int d = d0 + lane;                                         // distance from the leaf
                 if (d < plen) {
-                    const unsigned e = path[plen - 1 - d];
+                    const unsigned e = d0 == 0 ? e0 : path[plen - 1 - d];
                     const int node = (int)(e >> PATH_NODE_SHIFT), c = (int)(e & ((1u << PATH_NODE_SHIFT) - 1));
-                    const float val = d == 0 ? val0 : ((d & 1) ? val1 : val2);
+                    const float val = d == 0 ? val0 : ((d & 1) ? val1 : val2);   // value = 1 - value per ply (:313)
                     const size_t row = (size_t)node * G::AP;
-                    if (d == 0) t.cval[row + c] = val0;
+                    if (d == 0) t.cval[row + c] = val0;                          // :308
                     t.cvsum[row + c] = __fadd_rn(t.cvsum[row + c], val);
                     t.cvis[row + c] += 1; t.cvl[row + c] -= 1;
                     int* h = t.hdr + (size_t)node * H_STRIDE;

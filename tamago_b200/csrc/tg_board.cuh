@@ -299,10 +299,15 @@ __device__ inline void wb_prepare_analysis(const WBoard<N>& b, WAnalysis<N>& an,
 
 struct PointStatus { bool legal_pre; bool need_scan; u64 h; int satari; bool eye; };
 
+// eye colour of a 3x3 code (board/pattern.py:53-98): byte table in global memory, or the same table packed to two bits per
+// code (16 KB) so that it fits in shared memory next to the boards
+struct EyeLutGlobal { const uint8_t* __restrict__ t; __device__ __forceinline__ int operator()(unsigned p) const { return t[p]; } };
+struct EyeLutPacked { const uint32_t* t; __device__ __forceinline__ int operator()(unsigned p) const { return (int)((t[p >> 4] >> ((p & 15u) * 2)) & 3u); } };
+
 // Lane-local part of is_legal / check_self_atari_stone / is_complete_eye for one point.
-template <int N>
+template <int N, class EyeFn>
 __device__ inline PointStatus wb_point_status(const WBoard<N>& b, const WAnalysis<N>& an, const BScal& s, int pos, int color, bool superko,
-                                              const u64* __restrict__ zob, const uint8_t* __restrict__ eye_lut)
+                                              const u64* __restrict__ zob, const EyeFn& eye_lut)
 {
     using G = Geo<N>;
     PointStatus r; r.legal_pre = false; r.need_scan = false; r.h = 0; r.satari = 0; r.eye = false;
@@ -368,14 +373,14 @@ __device__ inline PointStatus wb_point_status(const WBoard<N>& b, const WAnalysi
     // is_complete_eye (go_board.py:367-397)
     {
         bool eye = false;
-        if (eye_lut[pat3_at(b, pos)] == color) {
+        if (eye_lut(pat3_at(b, pos)) == color) {
             const int x4[4] = { pos - G::W - 1, pos - G::W + 1, pos + G::W - 1, pos + G::W + 1 };
             int cnt = 0; bool edge = false;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int cc = b.color[x4[i]];
                 if (cc == color || cc == OB) cnt++;
-                else if (cc == EMPTY && eye_lut[pat3_at(b, x4[i])] == color) cnt++;
+                else if (cc == EMPTY && eye_lut(pat3_at(b, x4[i])) == color) cnt++;
                 if (cc == OB) edge = true;
             }
             eye = (edge && cnt == 4) || (!edge && cnt >= 3);
@@ -409,7 +414,7 @@ __device__ inline void wb_analyze(const WBoard<N>& b, WAnalysis<N>& an, const BS
         const int idx = base + lane;
         PointStatus st; st.legal_pre = false; st.need_scan = false; st.h = 0; st.satari = 0; st.eye = false;
         int pos = 0;
-        if (idx < G::NN) { pos = onboard_pos<N>(idx); st = wb_point_status(b, an, s, pos, color, superko, zob, eye_lut); }
+        if (idx < G::NN) { pos = onboard_pos<N>(idx); st = wb_point_status<N>(b, an, s, pos, color, superko, zob, EyeLutGlobal{eye_lut}); }
         bool legal = st.legal_pre;
         unsigned m = __ballot_sync(0xffffffffu, legal && st.need_scan);
         while (m) {
@@ -489,6 +494,50 @@ __device__ inline int wb_count_score(const WBoard<N>& b, uint8_t* tmp /*CP bytes
     }
     __syncwarp();
     return __shfl_sync(0xffffffffu, score, 0);
+}
+
+// Tromp-Taylor area score, Black - White: stones plus the empty regions that reach one colour only --
+// the adjudication the reference's get_final_status.py:15-64 obtains from GNU Go over a pipe, as a warp flood fill on the
+// shared-memory board.  Regions are labelled by min-label propagation (every sweep lowers each empty point to the
+// smallest label among its empty neighbours until nothing changes), then each region ORs the colours it touches.
+//   lab: CP uint16 of scratch, reach: CP unsigned of scratch.
+template <int N>
+__device__ inline int wb_tromp_taylor(const WBoard<N>& b, uint16_t* lab, unsigned* reach, int lane)
+{
+    using G = Geo<N>;
+    for (int c = lane; c < G::CP; c += 32) { lab[c] = (c < G::CELLS && b.color[c] == EMPTY) ? (uint16_t)c : (uint16_t)0xffff; reach[c] = 0; }
+    __syncwarp();
+    for (;;) {
+        bool changed = false;
+        for (int c = lane; c < G::CELLS; c += 32) {
+            if (b.color[c] != EMPTY) continue;
+            const int q[4] = { c - G::W, c - 1, c + 1, c + G::W };
+            unsigned m = lab[c];
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (b.color[q[i]] == EMPTY) m = min(m, (unsigned)lab[q[i]]);
+            if (m < lab[c]) { lab[c] = (uint16_t)m; changed = true; }
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+    for (int c = lane; c < G::CELLS; c += 32) {
+        if (b.color[c] != EMPTY) continue;
+        const int q[4] = { c - G::W, c - 1, c + 1, c + G::W };
+        unsigned r = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const int cc = b.color[q[i]]; if (cc == BLACK) r |= 1u; else if (cc == WHITE) r |= 2u; }
+        if (r) atomicOr(&reach[lab[c]], r);
+    }
+    __syncwarp();
+    int score = 0;
+    for (int c = lane; c < G::CELLS; c += 32) {
+        const int cc = b.color[c];
+        if (cc == BLACK) score++;
+        else if (cc == WHITE) score--;
+        else if (cc == EMPTY) { const unsigned r = reach[lab[c]]; score += (r == 1u) - (r == 2u); }
+    }
+    __syncwarp();
+    return warp_sum_i(score);
 }
 
 }  // namespace tg

@@ -69,6 +69,7 @@ struct tg_engine {
     int64_t last_eval_slots = 0;
     int sms = 148;
     bool puct_warp = false;
+    const uint32_t* eye2 = nullptr;              // eye table packed to two bits per code (block-per-game kernels keep it in shared memory)
 };
 
 template <class T> static int dalloc(tg_engine* e, T** p, size_t n, bool zero = true)
@@ -148,11 +149,11 @@ template <int BN> static int setup_kernel_attrs()
     CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return 0;
 }
-constexpr int PUCT_NT = 256;              // threads per game in the block-per-game PUCT kernels: 1024 games = one wave of 8 CTAs per SM
 template <int BN> static int setup_blk_attr()
 {
-    static_assert(sizeof(BlkSmem<BN, PUCT_NT>) <= 48 * 1024, "block-per-game scratch fits the default shared-memory window");
-    CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, PUCT_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    static_assert(sizeof(BlkSmem<BN, 512>) <= 96 * 1024, "block-per-game scratch");
+    CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem<BN, 256>)));
+    CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem<BN, 512>)));
     return 0;
 }
 template <int BN, int G> static int setup_tc_attr()
@@ -242,6 +243,7 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     for (auto& ev : e->events) if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "event"));
 
     Dev& D = e->D;
+    D.scoring = cfg->scoring;
     D.games = games; D.superko = cfg->superko; D.cgos = cfg->cgos_mode; D.dedup = cfg->dedup; D.seed = cfg->seed;
     D.cap = e->cap_sh; D.max_depth = e->depth_sh; D.slot_cap = e->slot_cap;
     D.tree.max_nodes = max_nodes;
@@ -305,7 +307,19 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     if (rc) return bail(rc);
     DISPATCH_N(e, rc = setup_blk_attr<BN>());
     if (rc) return bail(rc);
-    e->puct_warp = getenv("TG_PUCT_WARP") != nullptr;
+    // PUCT kernels: one warp per game when the pool fills the machine with warps (throughput), one CTA per game when it
+    // does not (latency): BASELINE configs[3] (1024 games) runs warp-per-game, configs[4] (one game) block-per-game
+    e->puct_warp = getenv("TG_PUCT_WARP") != nullptr || (games > 3 * e->sms && getenv("TG_PUCT_BLOCK") == nullptr);
+    {
+        std::vector<uint8_t> tab; build_eye_table(tab);
+        std::vector<uint32_t> packed(4096, 0u);
+        for (int i = 0; i < 65536; i++) packed[i >> 4] |= (uint32_t)(tab[i] & 3u) << ((i & 15) * 2);
+        uint32_t* q = nullptr;
+        if ((rc = dalloc(e, &q, 4096, false)) != 0) return bail(rc);
+        if (cudaMemcpyAsync(q, packed.data(), 4096 * 4, cudaMemcpyHostToDevice, e->stream) != cudaSuccess || cudaStreamSynchronize(e->stream) != cudaSuccess)
+            return bail(fail(TG_ERR_CUDA, "eye table upload"));
+        e->eye2 = q;
+    }
 
     // default Zobrist table (splitmix64 stream); tg_set_zobrist replaces it
     {
@@ -521,6 +535,7 @@ extern "C" int tg_play(tg_engine* e, const int16_t* moves, const uint8_t* colors
         bad |= da((void**)&pd.scal, np * 5 * 4); bad |= da((void**)&pd.hash, np * 8);
         bad |= da((void**)&pd.legal, np * 2 * e->NN); bad |= da((void**)&pd.satari, np * 2 * e->NN * 2);
         bad |= da((void**)&pd.eye, np * 2 * e->NN); bad |= da((void**)&pd.cand, np * 2 * e->NN); bad |= da((void**)&pd.score, np * 4);
+        if (dump->tt_score) bad |= da((void**)&pd.tt_score, np * 4);
         pd.stride = plies;
     }
     if (bad) return fail(TG_ERR_CUDA, "temporary allocation failed");
@@ -534,7 +549,7 @@ extern "C" int tg_play(tg_engine* e, const int16_t* moves, const uint8_t* colors
 #define CP_OUT(field, bytes) if (dump->field) CK(cudaMemcpyAsync(dump->field, pd.field, (bytes), cudaMemcpyDeviceToHost, e->stream))
         CP_OUT(color, np * e->CELLS); CP_OUT(libs, np * e->CELLS * 2); CP_OUT(size, np * e->CELLS * 2); CP_OUT(scal, np * 5 * 4);
         CP_OUT(hash, np * 8); CP_OUT(legal, np * 2 * e->NN); CP_OUT(satari, np * 2 * e->NN * 2); CP_OUT(eye, np * 2 * e->NN);
-        CP_OUT(cand, np * 2 * e->NN); CP_OUT(score, np * 4);
+        CP_OUT(cand, np * 2 * e->NN); CP_OUT(score, np * 4); CP_OUT(tt_score, np * 4);
 #undef CP_OUT
     }
     CK(cudaStreamSynchronize(e->stream));
@@ -649,10 +664,14 @@ extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int3
                         k_descend_puct<BN><<<grid, thr, sm, e->stream>>>(D, visits, batch, strict);
                         rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
                         k_backup<BN><<<grid, thr, 0, e->stream>>>(D, 0);
-                    } else {                             // block-per-game: a ply runs PUCT_NT threads wide (tg_block.cuh)
-                        k_descend_puct_blk<BN, PUCT_NT><<<games, PUCT_NT, sizeof(BlkSmem<BN, PUCT_NT>), e->stream>>>(D, visits, batch, strict);
+                    } else if (games <= e->sms) {        // block-per-game, 512 threads per ply (tg_block.cuh): single-game genmove
+                        k_descend_puct_blk<BN, 512><<<games, 512, sizeof(BlkSmem<BN, 512>), e->stream>>>(D, e->eye2, visits, batch, strict);
                         rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
-                        k_backup_blk<BN, PUCT_NT><<<games, PUCT_NT, 0, e->stream>>>(D, 0);
+                        k_backup_blk<BN, 512><<<games, 512, 0, e->stream>>>(D, 0);
+                    } else {                             // block-per-game, 256 threads: up to three CTAs per SM
+                        k_descend_puct_blk<BN, 256><<<games, 256, sizeof(BlkSmem<BN, 256>), e->stream>>>(D, e->eye2, visits, batch, strict);
+                        rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
+                        k_backup_blk<BN, 256><<<games, 256, 0, e->stream>>>(D, 0);
                     }
                     e->launches += 2;
                 }

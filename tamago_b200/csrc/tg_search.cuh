@@ -33,6 +33,7 @@ constexpr int PATH_NODE_SHIFT = 12;       // path entry: node << 12 | child
 // Everything the search kernels need, passed by value.
 struct Dev {
     int games, cap, max_depth, superko, cgos, dedup;
+    int scoring;             // 0: GoBoard.count_score (the reference), 1: Tromp-Taylor area score (tg_config.scoring)
     u64 seed;
     // root boards
     uint8_t* b_color; uint16_t* b_chain; unsigned* b_bloom; u64* b_hash; int* b_scal; u64* hist_hash; int16_t* hist_pos;
@@ -591,7 +592,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_move_end(Dev D, int mode,
     if (lane == 0) { gs[GS_PASSCNT] = pass_count; gs[GS_NMOVES] = nmoves; gs[GS_COLOR] = opp(color); }
     if (pass_count == 2) {                                                       // :76-87
         uint8_t* tmp = reinterpret_cast<uint8_t*>(sm.scratch.color);
-        const int sc = wb_count_score<N>(sm.root, tmp, lane);
+        const int sc = D.scoring == 1 ? wb_tromp_taylor<N>(sm.root, sm.scratch.chain, sm.scratch.ls, lane)
+                                      : wb_count_score<N>(sm.root, tmp, lane);                   // worker.py:81
         const float score = (float)sc - komi;
         if (lane == 0) {
             gs[GS_SCORE] = __float_as_int(score);
@@ -642,6 +644,7 @@ struct PlyDump {
     uint8_t* eye;        // [games][plies][2][NN]
     uint8_t* cand;       // [games][plies][2][NN]
     int* score;          // [games][plies]
+    int* tt_score;       // [games][plies]   Tromp-Taylor area score (optional)
     int stride;          // plies allocated per game
 };
 
@@ -697,6 +700,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_play(Dev D, const int16_t
             uint8_t* tmp = reinterpret_cast<uint8_t*>(sm.scratch.color);
             const int score = wb_count_score<N>(sm.root, tmp, lane);
             if (lane == 0) dump.score[pi] = score;
+            if (dump.tt_score) {
+                const int tts = wb_tromp_taylor<N>(sm.root, sm.scratch.chain, sm.scratch.ls, lane);
+                if (lane == 0) dump.tt_score[pi] = tts;
+            }
         }
     }
     wb_store<N>(sm.root, s, pool_of<N>(D), g, lane);

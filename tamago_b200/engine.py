@@ -97,11 +97,11 @@ class Engine:
             out = dict(color=np.zeros((g, p, c), np.uint8), libs=np.zeros((g, p, c), np.int16), size=np.zeros((g, p, c), np.int16),
                        scal=np.zeros((g, p, 5), np.int32), hash=np.zeros((g, p), np.uint64), legal=np.zeros((g, p, 2, n2), np.uint8),
                        satari=np.zeros((g, p, 2, n2), np.int16), eye=np.zeros((g, p, 2, n2), np.uint8),
-                       cand=np.zeros((g, p, 2, n2), np.uint8), score=np.zeros((g, p), np.int32))
+                       cand=np.zeros((g, p, 2, n2), np.uint8), score=np.zeros((g, p), np.int32), tt_score=np.zeros((g, p), np.int32))
             d = _lib.PlyDump(_ptr(out["color"], C.c_uint8), _ptr(out["libs"], C.c_int16), _ptr(out["size"], C.c_int16),
                              _ptr(out["scal"], C.c_int32), _ptr(out["hash"], C.c_uint64), _ptr(out["legal"], C.c_uint8),
                              _ptr(out["satari"], C.c_int16), _ptr(out["eye"], C.c_uint8), _ptr(out["cand"], C.c_uint8),
-                             _ptr(out["score"], C.c_int32), p)
+                             _ptr(out["score"], C.c_int32), p, _ptr(out["tt_score"], C.c_int32))
         check(self.lib.tg_play(self.h, _ptr(mv, C.c_int16), None if col is None else _ptr(col, C.c_uint8),
                                _ptr(cnt, C.c_int32), stride, None if d is None else C.byref(d)))
         return out

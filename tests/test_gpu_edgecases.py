@@ -214,3 +214,48 @@ def test_pass_pass_and_move_limit_endings():
                     assert step == 2 * size * size - 1 and int(r["winner"][k]) == 0
     assert done.all()
     e.close()
+
+
+def test_tromp_taylor_scorer_on_device():
+    """the device flood-fill area scorer (tg_config.scoring = 1; default stays count_score)
+    against the oracle's flood fill on every ply of random games, and as the terminal score of finished self-play games."""
+    import tamago_b200 as tb
+    from oracle import oracle as orc
+    for size, ng, plies in ((9, 32, 140), (19, 6, 500)):
+        zob, moves, boards, _ = _random_games(orc, size, ng, plies, seed=31 + size, p_any_legal=0.4)
+        e = tb.Engine(board_size=size, games=ng, max_visits=4, superko=True, evaluator=tb.EVAL_HASHNET)
+        e.set_zobrist(zob)
+        d = e.play(moves, dump=True)
+        differ = 0
+        for k in range(ng):
+            b = orc.OracleBoard(size, 7.0, True, zob)
+            color = 1
+            for i in range(plies):
+                b.put_stone(int(moves[k, i]), color); color = 3 - color
+                if i % 5 == 4 or i == plies - 1:
+                    assert int(d["tt_score"][k, i]) == b.tromp_taylor(), (size, k, i)
+                    differ += int(d["tt_score"][k, i]) != int(d["score"][k, i])
+        assert differ > 0                       # the two scorers are different functions of the position
+        e.close()
+    # terminal scoring of self-play games under both settings
+    size, ng, visits = 9, 6, 16
+    zob = orc.default_zobrist(size)
+    for scoring in (0, 1):
+        e = tb.Engine(board_size=size, games=ng, max_visits=visits, superko=True, evaluator=tb.EVAL_HASHNET, seed=4, scoring=scoring)
+        e.set_zobrist(zob)
+        e.reset(never_resign=np.ones(ng, np.uint8))
+        boards = [orc.OracleBoard(size, 7.0, True, zob) for _ in range(ng)]
+        done = np.zeros(ng, bool)
+        for step in range(2 * size * size):
+            r = e.genmove(mode=tb.MODE_SH, visits=visits, play=True)
+            for k in range(ng):
+                if done[k]:
+                    continue
+                boards[k].put_stone(int(r["move"][k]), int(r["color"][k]))
+                if r["finished"][k]:
+                    done[k] = True
+                    if int(r["winner"][k]) != 0:
+                        want = (boards[k].tromp_taylor() if scoring else boards[k].count_score()) - 7.0
+                        assert abs(float(r["score"][k]) - want) < 1e-6, (scoring, k)
+        assert done.all()
+        e.close()

@@ -93,3 +93,60 @@ def test_c4_full_games_19x19_puct400_vs_oracle(batch):
         assert final[g][0] == winner and final[g][1] == int(is_resign) and abs(final[g][2] - score) < 1e-6, g
         total += len(pos)
     assert total > ng * 60
+
+
+def test_puct_kernel_variants_agree(monkeypatch):
+    """The three PUCT descent/backup kernels (warp per game; CTA per game with 256 or 512 threads) are bit-identical:
+    160 positions (-> 256-thread CTAs by default), 100 (-> 512-thread CTAs) and the warp kernels forced by TG_PUCT_WARP,
+    batch 1 and batch 16 (tentative priors, duplicate leaves), compared on every root statistic; a sample against the oracle."""
+    import tamago_b200 as tb
+    from oracle import oracle as orc
+    size = 13
+    rs = np.random.RandomState(23)
+    zob = orc.default_zobrist(size)
+    boards, mls = [], []
+    for k in range(160):
+        b = orc.OracleBoard(size, 7.0, True, zob)
+        color, ml = orc.BLACK, []
+        for _ in range(int(rs.randint(0, 150))):
+            cand = b.candidates(color)
+            pos = int(rs.choice(cand[:-1])) if len(cand) > 1 and rs.rand() > 0.03 else 0
+            b.put_stone(pos, color); ml.append(pos); color = 3 - color
+        boards.append((b, color)); mls.append(ml)
+
+    def run(ng, batch, visits, dedup, warp):
+        if warp:
+            monkeypatch.setenv("TG_PUCT_WARP", "1")
+        else:
+            monkeypatch.delenv("TG_PUCT_WARP", raising=False)
+        e = tb.Engine(board_size=size, games=ng, max_visits=visits, superko=True, batch_size=batch, evaluator=tb.EVAL_HASHNET2,
+                      dedup=dedup, seed=3)
+        e.set_zobrist(zob)
+        mp = max(1, max(len(m) for m in mls[:ng]))
+        moves = np.zeros((ng, mp), np.int16)
+        for k, m in enumerate(mls[:ng]):
+            moves[k, :len(m)] = m
+        e.play(moves, np.array([len(m) for m in mls[:ng]], np.int32))
+        res = e.genmove(mode=tb.MODE_PUCT, visits=visits, play=False)
+        assert (res["error"] == 0).all()
+        roots = [e.node(k, 0) for k in range(0, ng, 7)]
+        sizes = [e.tree_size(k) for k in range(ng)]
+        e.close()
+        return res, roots, sizes
+
+    for batch, visits, dedup in ((1, 48, False), (16, 90, True)):
+        ref = run(160, batch, visits, dedup, warp=True)
+        for ng in (160, 100):
+            got = run(ng, batch, visits, dedup, warp=False)
+            assert np.array_equal(got[0]["move"], ref[0]["move"][:ng]) and np.array_equal(got[0]["visits"], ref[0]["visits"][:ng])
+            assert got[2] == ref[2][:ng]
+            for a, b in zip(got[1], ref[1]):
+                for key in ("children_visits", "children_value_sum", "children_policy", "children_index", "children_virtual_loss"):
+                    assert np.array_equal(a[key], b[key]), (ng, batch, key)
+        for k in range(0, 160, 40):
+            b, color = boards[k]
+            t = orc.OracleTree(size, orc.hashnet2, tree_size=4096, batch_size=batch)
+            t.set_noise_key(3, k, b.moves)
+            mv = t.genmove_puct(b, color, visits, False)
+            assert ref[0]["move"][k] in (mv, -1) and ref[2][k] == t.num_nodes
+            assert np.array_equal(ref[0]["visits"][k, :t.node(0)["num_children"]], t.node(0)["children_visits"])
