@@ -8,7 +8,7 @@ mode sh   : calls the reference's selfplay.worker.selfplay_worker(save_dir, <mis
             selfplay/worker.py:72); a watchdog ends the process after T seconds (a 400-visit game takes minutes).
 mode puct : the same game loop around MCTSTree.search_best_move (mcts/tree.py:57) with CONSTANT_PLAYOUT, i.e. what
             gtp/client.py:215-219 runs per genmove -- the reference has no PUCT self-play entry point.
-Prints one JSON line: {"moves": n, "first": t_first_move_done, "last": t_last_move_done, "start": t_start}.
+Prints one JSON line: {"moves": n, "first": t_first_move_done, "last": t_last_move_done, "start": t_start[, "stamps": [...]]}.
 One torch thread per worker (OMP_NUM_THREADS=1): the fan-out is one process per core like selfplay_main.py:58.
 """
 import argparse
@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=20.0)
     ap.add_argument("--index", type=int, default=1)
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--stamps", type=int, default=0, help="1: also print the wall-clock stamp of every root move")
     a = ap.parse_args()
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     sys.dont_write_bytecode = True
@@ -44,8 +45,10 @@ def main():
     t_start = time.time()
 
     def finish():
-        line = json.dumps({"moves": len(stamps), "first": stamps[0] if stamps else None,
-                           "last": stamps[-1] if stamps else None, "start": t_start}) + "\n"
+        d = {"moves": len(stamps), "first": stamps[0] if stamps else None, "last": stamps[-1] if stamps else None, "start": t_start}
+        if a.stamps:
+            d["stamps"] = list(stamps)
+        line = json.dumps(d) + "\n"
         os.write(1, line.encode())                                  # fd 1 directly: sys.stdout is muted while the reference runs
         os._exit(0)
 

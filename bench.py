@@ -118,7 +118,7 @@ def reference_run(mode, size, visits, procs, warm_s, steps, step_s, batch=1):
     # workers start their clocks after the imports; the window opens warm_s after the LAST worker started
     t0 = max(starts) + warm_s
     st = np.array(sorted(stamps))
-    t_end = min(t0 + steps * step_s, max(starts) - 0.0 + total - 0.5) if len(st) else t0
+    t_end = min(t0 + steps * step_s, min(starts) + total - 0.2)      # every worker is still playing until then
     eff_step = (t_end - t0) / steps
     per_step = [int(((st >= t0 + i * eff_step) & (st < t0 + (i + 1) * eff_step)).sum()) for i in range(steps)]
     moves = sum(per_step)
@@ -261,22 +261,23 @@ def run_ours(a, out=sys.stdout):
         pool.start()
         if preage:
             pool.preage(max_age=int(1.4 * size * size), seed=rank)
-        for _ in range(warm):
-            pool.step()
+        for i in range(warm):
+            pool.step(queue_next=i + 1 < warm)               # nothing is in flight when the clock starts
         barrier()
         l0, f0, fm0 = pool.eng.launches, pool.files, pool.file_moves
         dev_ms = eval_ms = 0.0
         moves = evals = 0
         t0 = time.perf_counter()
         for i in range(steps):
-            m, nf = pool.step(queue_next=True)
+            # step(): queue a step if none is in flight, wait for it, fetch finished records, reset + refill, queue the NEXT step,
+            # write the SGF files while it runs.  The last timed step queues nothing: every step's work lies inside [t0, t1].
+            m, nf = pool.step(queue_next=i + 1 < steps)
             moves += m
             dev_ms += pool.eng.last_device_ms
             eval_ms += pool.eng.bench_kernel("eval_ms")
             evals += int(pool.last["evals"][1])
-        # the step queued behind the last collected one is not part of the timed region's work: drain it untimed
-        wall = time.perf_counter() - t0
         barrier()
+        wall = time.perf_counter() - t0
         res = dict(dev_ms=dev_ms, eval_ms=eval_ms, wall=wall, moves=moves, evals=evals, launches=pool.eng.launches - l0,
                    files=pool.files - f0, file_moves=pool.file_moves - fm0, stride=pool.eng.stride)
         pool.close()

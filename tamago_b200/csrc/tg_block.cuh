@@ -89,19 +89,32 @@ __device__ __forceinline__ void blk_sum_max(BlkSmem<N, NT>& sm, Blk<NT>& k, int&
     for (int w = 0; w < NT / 32; w++) { ss += sm.r_i[p][w]; mm = max(mm, sm.r_j[p][w]); }
     s = ss; mx = mm;
 }
-// argmax with numpy semantics (first index wins ties); idx = INT_MAX marks an empty thread
+// argmax with numpy semantics (first index wins ties); idx = INT_MAX marks an empty thread.
+//   Doubles are mapped to order-preserving 64-bit integer keys, so the warp stage is three REDUX instructions (max of the
+//   high words, max of the low words among the holders of that maximum, min of the indices among the holders of both)
+//   instead of a five-round shuffle butterfly on (double, index) pairs -- measured 2.5 k -> see profiles/r02_puct_block.md.
+__device__ __forceinline__ u64 order_key(double v)
+{
+    const u64 b = (u64)__double_as_longlong(v == 0.0 ? 0.0 : v);              // -0.0 and +0.0 compare equal
+    return b ^ ((u64)((long long)b >> 63) | 0x8000000000000000ull);
+}
 template <int N, int NT>
 __device__ __forceinline__ int blk_argmax_d(BlkSmem<N, NT>& sm, Blk<NT>& k, double v, int idx)
 {
-    warp_argmax_d(v, idx);
+    const bool have = idx != 0x7fffffff;
+    const u64 key = have ? order_key(v) : 0ull;                               // real keys are never 0 (no NaNs in the scores)
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const unsigned mi = __reduce_min_sync(0xffffffffu, (have && hi == mhi && lo == mlo) ? (unsigned)idx : 0x7fffffffu);
     const int p = k.ph; k.ph ^= 1;
-    if (k.lane == 0) { sm.r_d[p][k.warp] = v; sm.r_i[p][k.warp] = idx; }
+    if (k.lane == 0) { sm.r_x[p][k.warp] = ((u64)mhi << 32) | mlo; sm.r_i[p][k.warp] = (int)mi; }
     k.sync();
-    double bv = sm.r_d[p][0]; int bi = sm.r_i[p][0];
+    u64 bk = sm.r_x[p][0]; int bi = sm.r_i[p][0];
 #pragma unroll
     for (int w = 1; w < NT / 32; w++) {
-        const double ov = sm.r_d[p][w]; const int oi = sm.r_i[p][w];
-        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        const u64 ok = sm.r_x[p][w]; const int oi = sm.r_i[p][w];
+        if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
     }
     return bi;
 }
@@ -302,8 +315,9 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;"
 
 // ---- selection (node.py:141-157 + pucb.py:8-29) on a staged node: one child per thread -----------------------------------
 template <int N, int NT>
-__device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const typename BlkSmem<N, NT>::NodeStage& st, bool cgos, Blk<NT>& k)
+__device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const typename BlkSmem<N, NT>::NodeStage& st, bool cgos, Blk<NT>& k, long long* prof = nullptr)
 {
+    long long c0 = prof ? clock64() : 0;
     const int nk = st.hdr[H_K];
     const double sq = sqrt((double)(st.hdr[H_NV] + st.hdr[H_VL] + 1));
     double bv = 0.0; int bi = 0x7fffffff;
@@ -315,7 +329,10 @@ __device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const typename BlkSmem
         if (cgos && i == nk - 1) v = dsub(v, 0.1);
         if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
     }
-    return blk_argmax_d<N, NT>(sm, k, bv, bi);
+    if (prof) { const long long c = clock64(); prof[8] += c - c0; c0 = c; }
+    const int r = blk_argmax_d<N, NT>(sm, k, bv, bi);
+    if (prof) { const long long c = clock64(); prof[9] += c - c0; }
+    return r;
 }
 
 // ---- expansion (tree.py:247-270 + node.py:41-72) ------------------------------------------------------------------
@@ -517,7 +534,7 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, const uint32_t* 
         bool fail = false;
         for (;;) {
             const typename BlkSmem<N, NT>::NodeStage& st = sm.st[buf];
-            const int next = select_puct_blk<N, NT>(sm, st, D.cgos != 0, k);         // :213
+            const int next = select_puct_blk<N, NT>(sm, st, D.cgos != 0, k, prof ? D.prof : nullptr);         // :213
             if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
             const size_t row = (size_t)cur * G::AP;
             const int mv = st.action[next];
@@ -561,8 +578,10 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, const uint32_t* 
             }
             cur = ci; buf ^= 1;
             if (plen >= D.max_depth) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_DEPTH; fail = true; break; }
+            if (prof) pt0 = clock64();
             stage_wait();
             k.sync();                                        // the child's rows are in shared memory
+            if (prof) { const long long c = clock64(); D.prof[10] += c - pt0; pt0 = c; }
         }
         __threadfence_block();
         k.sync();

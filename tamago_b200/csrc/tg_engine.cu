@@ -711,8 +711,9 @@ extern "C" int tg_collect(tg_engine* e, tg_step_result* out)
         long long h[16];
         CK(cudaMemcpy(h, D.prof, sizeof h, cudaMemcpyDeviceToHost));
         CK(cudaMemset(D.prof, 0, 64 * sizeof(long long)));
-        fprintf(stderr, "descend profile (game 0, cycles): copy %lld  select %lld (%lld)  put_stone %lld  expand %lld (%lld)  push_leaf %lld (%lld)\n",
-                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7]);
+        fprintf(stderr, "descend profile (game 0, cycles): copy %lld  select %lld (%lld)  put_stone %lld  expand %lld (%lld)  push_leaf %lld (%lld)"
+                        "  [select: scores %lld  argmax %lld  row wait %lld]\n",
+                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7], h[8], h[9], h[10]);
     }
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
     e->last_eval_ms = 0.f;

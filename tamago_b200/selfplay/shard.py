@@ -22,6 +22,13 @@ def shard_for_rank(num_data, rank=None, world=None):
     return parts[rank] if rank < len(parts) else []
 
 
+def shard_offset(rank=None, span=10_000_000):
+    """First game index (minus one) of a rank when ranks take disjoint, contiguous index ranges of `span` games each:
+    open-ended runs (benchmarks, continuous self-play) where num_data is not known in advance."""
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    return rank * span
+
+
 def reduce_counters(moves, seconds, device=None):
     """Whole-job moves and the slowest rank's time (max over ranks): moves/sec = sum(moves) / max(seconds)."""
     import torch

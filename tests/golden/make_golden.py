@@ -530,6 +530,74 @@ def numpy_weights(size, seed):
     return sd
 
 
+def train_data_set(size, seed, samples):
+    """Seeded synthetic rl_data npz (layout of nn/data_generator.py:16-33): one-hot stone planes, a last-move plane, colour
+    plane, improved-policy-like targets (softmax of Gumbel noise over a random support, 1e-18 elsewhere) and value labels."""
+    rs = np.random.RandomState(seed)
+    nn_ = size * size
+    cls = rs.randint(0, 3, (samples, size, size))
+    x = np.zeros((samples, 6, size, size), np.float32)
+    for c in range(3):
+        x[:, c] = cls == c
+    last = rs.randint(0, nn_, samples)
+    x.reshape(samples, 6, nn_)[np.arange(samples), 3, last] = 1.0
+    x[:, 5] = np.where(rs.rand(samples) < 0.5, 1.0, -1.0)[:, None, None]
+    logits = rs.gumbel(size=(samples, nn_ + 1)) * 2.0
+    support = rs.rand(samples, nn_ + 1) < 0.4
+    support[:, -1] = True
+    p = np.where(support, np.exp(logits), 0.0)
+    p = p / p.sum(axis=1, keepdims=True)
+    policy = np.where(support, p, 1e-18).astype(np.float64)
+    value = rs.randint(0, 3, samples).astype(np.int32)
+    return dict(input=x, policy=policy, value=value, kifu_count=np.array(samples // 8))
+
+
+def gen_train(size, out, weight_seed=515, data_seed=616, perm_seed=717, batch=64, steps=4):
+    """K mini-batches of the reference's own train_with_gumbel_alphazero_on_cpu (nn/learn.py:234-315) from a seeded model
+    and data set; records the per-step losses and, per tensor of the saved rl-model.bin, 64 sampled entries + the L1 norm."""
+    import tempfile
+    import torch
+    import nn.learn as learn
+    torch.set_num_threads(2)
+    tmp = tempfile.mkdtemp()
+    os.makedirs(os.path.join(tmp, "data")); os.makedirs(os.path.join(tmp, "model"))
+    samples = batch * steps
+    np.savez_compressed(os.path.join(tmp, "data", "rl_data_0.npz"), **train_data_set(size, data_seed, samples))
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in numpy_weights(size, weight_seed).items()}
+    torch.save(sd, os.path.join(tmp, "model", "rl-model.bin"))
+    losses = []
+    orig_kld, orig_val = learn.calculate_policy_kld_loss, learn.calculate_value_loss
+    state = {}
+
+    def kld(o, t):
+        state["p"] = orig_kld(o, t)
+        return state["p"]
+
+    def val(o, t):
+        v = orig_val(o, t)
+        losses.append([float((state["p"] + v).mean()), float(state["p"]), float(v.mean())])
+        return v
+    learn.calculate_policy_kld_loss, learn.calculate_value_loss = kld, val          # pass-through probes (values only)
+    np.random.seed(perm_seed)
+    torch.set_grad_enabled(True)
+    learn.train_with_gumbel_alphazero_on_cpu(tmp, size, batch)
+    learn.calculate_policy_kld_loss, learn.calculate_value_loss = orig_kld, orig_val
+    final = torch.load(os.path.join(tmp, "model", "rl-model.bin"))
+    rs = np.random.RandomState(1)
+    names, idxs, vals, sums = [], [], [], []
+    for k, v in final.items():
+        t = v.double().reshape(-1).numpy()
+        idx = rs.randint(0, 1 << 30, 64)
+        sel = idx[:min(len(t), 64)] % len(t)
+        pad = np.zeros(64); pad[:len(sel)] = t[sel]
+        names.append(k); idxs.append(idx); vals.append(pad); sums.append(np.abs(t).sum())
+    np.savez_compressed(out, size=size, weight_seed=weight_seed, data_seed=data_seed, perm_seed=perm_seed, batch=batch, steps=steps,
+                        samples=samples, losses=np.array(losses), names=np.array(names), sample_idx=np.array(idxs),
+                        sample_val=np.array(vals), abs_sum=np.array(sums))
+    shutil.rmtree(tmp)
+    print(f"train golden: {steps} steps, losses {np.array(losses)[:, 0]} -> {out}")
+
+
 def gen_dualnet(size, seed, board_npz, out):
     import torch
     from nn.network.dual_net import DualNet
@@ -620,6 +688,8 @@ def main():
             fixed = [ml[0], ml[1], next(m for m in mid[1:] if len(m) >= 60)[:60]]
             gen_search2(N, 80, out, 0, [(400, 1)], [(400, 1, 1, 0), (400, 8, 1, 0), (1600, 256, 1, 0), (1600, 256, 0, 1)],
                         fixed_positions=fixed)
+    if want("train") and N == 9:
+        gen_train(N, os.path.join(HERE, "train_9.npz"))
     if want("modelbin") and N == 9:
         gen_modelbin(N, 2026, os.path.join(HERE, "board_9.npz"), os.path.join(HERE, "model_ref_9.bin"),
                      os.path.join(HERE, "model_ref_9.npz"))
