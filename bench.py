@@ -265,6 +265,7 @@ def run_ours(a, out=sys.stdout):
             pool.step(queue_next=i + 1 < warm)               # nothing is in flight when the clock starts
         barrier()
         l0, f0, fm0 = pool.eng.launches, pool.files, pool.file_moves
+        pool.timing = {k: 0.0 for k in pool.timing}
         dev_ms = eval_ms = 0.0
         moves = evals = 0
         t0 = time.perf_counter()
@@ -279,7 +280,8 @@ def run_ours(a, out=sys.stdout):
         barrier()
         wall = time.perf_counter() - t0
         res = dict(dev_ms=dev_ms, eval_ms=eval_ms, wall=wall, moves=moves, evals=evals, launches=pool.eng.launches - l0,
-                   files=pool.files - f0, file_moves=pool.file_moves - fm0, stride=pool.eng.stride)
+                   files=pool.files - f0, file_moves=pool.file_moves - fm0, stride=pool.eng.stride,
+                   host_ms_per_step={k: v / steps * 1e3 for k, v in pool.timing.items()})
         pool.close()
         shutil.rmtree(save_dir, ignore_errors=True)
         return res
@@ -392,7 +394,8 @@ def run_ours(a, out=sys.stdout):
         "data": "synthetic", "config": workload_config(a),
         "e2e": {"value": main["e2e"], "unit": "moves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": main["wall_ms_per_step"], "sgf_files_written": main["files"], "moves_in_files": main["file_moves"],
-                "api": "tamago_b200.selfplay.worker.SelfPlayPool.step (the loop body of selfplay_worker)"},
+                "api": "tamago_b200.selfplay.worker.SelfPlayPool.step (the loop body of selfplay_worker)",
+                "host_ms_per_step": main_raw["host_ms_per_step"]},
         "gpu_launches": main["launches"],
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "k_dualnet_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

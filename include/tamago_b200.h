@@ -47,6 +47,7 @@ typedef struct tg_config {
     int32_t net_blocks;       /* DualNet residual blocks (nn/network/dual_net.py:26), default 6 */
     uint64_t seed;            /* seed of the counter-based Dirichlet/Gumbel stream */
     int32_t record_ring;      /* 1: keep the SelfPlayRecord of every running game on the device (sgf/selfplay_record.py:45-64) */
+    int32_t sample_cap;       /* > 0: room for that many training samples emitted from the record ring (tg_emit_samples) */
     int32_t scoring;          /* final score of finished games: 0 = GoBoard.count_score (go_board.py:561-608, the reference),
                                  1 = Tromp-Taylor area scoring (the adjudication get_final_status.py:15-64 asks GNU Go for) */
 } tg_config;
@@ -101,6 +102,7 @@ typedef struct tg_step_result {
     float*   score;         /* [games] count_score() - komi (worker.py:81)                                 */
     int32_t* error;         /* [games] search error bits (0 = ok)                                          */
     int64_t* evals;         /* [2] leaf evaluations requested by the search, evaluations executed (differ with dedup) */
+    int32_t* n_moves;       /* [games] root moves played so far in the running game (SGFReader.get_n_moves of its record) */
 } tg_step_result;
 
 /* One node of a game's tree (MCTSNode, mcts/node.py:18-39), for tree-parity tests and get_root(). */
@@ -186,6 +188,20 @@ int  tg_read_node(tg_engine* e, int32_t game, int32_t index, tg_node_view* out);
 int  tg_format_sgf(int32_t board_size, int32_t n_moves, const int32_t* moves, const int32_t* colors,
                    const int32_t* num_children, const int16_t* action, const double* improved, int32_t stride,
                    int32_t winner, int32_t resigned, double score, double komi, char* out, int32_t out_cap);
+
+/* Training samples straight from the record ring (nn/data_generator.py:89-149 without the SGF round trip): for each listed
+ * FINISHED game (after tg_collect, before the tg_reset that recycles its slot) the positions before the plies plies[i][0..8)
+ * (ascending, -1 padded) under the symmetries syms[i][0..8) (go_board.py:74-104) are appended to device-resident arrays
+ * input [count][6][N][N] f32 (nn/feature.py:10-57), policy [count][N*N+1] f64 (feature.py:80-102: improved policy, 1e-18
+ * elsewhere) and value [count] i32 (2 = side to move won, 1 = draw, 0 = lost).  Which plies / symmetries: the caller's draw
+ * (the reference uses np.random.permutation, data_generator.py:123-124).  Returns the new sample count.
+ * tg_sample_buffers exposes the device arrays (zero copy: train on them or gather them over NCCL), tg_samples_read copies a
+ * range to the host -- round_like_sgf = 1 applies float(f"{p:.3e}") to the policy entries, which makes the result bit-equal
+ * to what the reference's generator reads back from the SGF comments. */
+int64_t tg_emit_samples(tg_engine* e, const int32_t* games, int32_t n, const int32_t* plies, const int32_t* syms);
+int     tg_sample_buffers(tg_engine* e, float** input, double** policy, int32_t** value, int64_t* count, int64_t* cap);
+int     tg_samples_read(tg_engine* e, int64_t first, int64_t n, float* input, double* policy, int32_t* value, int32_t round_like_sgf);
+int     tg_samples_clear(tg_engine* e);
 
 /* instrumentation: kernels launched by this engine so far, and device milliseconds of the last tg_genmove */
 int64_t tg_launch_count(tg_engine* e);

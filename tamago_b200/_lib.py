@@ -17,7 +17,7 @@ class Config(C.Structure):
     _fields_ = [("board_size", C.c_int32), ("komi", C.c_float), ("superko", C.c_int32), ("games", C.c_int32),
                 ("max_visits", C.c_int32), ("batch_size", C.c_int32), ("max_nodes", C.c_int32), ("device", C.c_int32),
                 ("evaluator", C.c_int32), ("dedup", C.c_int32), ("cgos_mode", C.c_int32), ("net_blocks", C.c_int32),
-                ("seed", C.c_uint64), ("record_ring", C.c_int32), ("scoring", C.c_int32)]
+                ("seed", C.c_uint64), ("record_ring", C.c_int32), ("sample_cap", C.c_int32), ("scoring", C.c_int32)]
 
 
 class Weights(C.Structure):
@@ -36,7 +36,7 @@ class PlyDump(C.Structure):
 class StepResult(C.Structure):
     _fields_ = [("move", i32p), ("color", i32p), ("num_children", i32p), ("action", i16p), ("improved", f64p),
                 ("visits", i32p), ("finished", i32p), ("winner", i32p), ("resigned", i32p), ("score", f32p),
-                ("error", i32p), ("evals", i64p)]
+                ("error", i32p), ("evals", i64p), ("n_moves", i32p)]
 
 
 class NodeView(C.Structure):
@@ -69,6 +69,10 @@ EXPORTS = {
     "tg_format_records": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64, i64p]),
     "tg_write_records": (C.c_int64, [C.c_void_p, C.c_char_p, i64p]),
     "tg_fetched_record": (C.c_int, [C.c_void_p, C.c_int32, i32p, i16p, u8p, i16p, i16p, f64p]),
+    "tg_emit_samples": (C.c_int64, [C.c_void_p, i32p, C.c_int32, i32p, i32p]),
+    "tg_sample_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), i64p, i64p]),
+    "tg_samples_read": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, f32p, f64p, i32p, C.c_int32]),
+    "tg_samples_clear": (C.c_int, [C.c_void_p]),
     "tg_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_stream_signal": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_tree_size": (C.c_int, [C.c_void_p, C.c_int32, i32p]),

@@ -330,6 +330,10 @@ __device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const typename BlkSmem
         if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
     }
     if (prof) { const long long c = clock64(); prof[8] += c - c0; c0 = c; }
+#ifdef TG_PROF_FINE
+    k.sync();
+    if (prof) { const long long c = clock64(); prof[11] += c - c0; c0 = c; }
+#endif
     const int r = blk_argmax_d<N, NT>(sm, k, bv, bi);
     if (prof) { const long long c = clock64(); prof[9] += c - c0; }
     return r;

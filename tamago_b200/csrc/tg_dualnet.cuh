@@ -61,6 +61,7 @@ struct NetDev {
     const float* w32_stem;       // [6 ic][9][64 oc]
     const float* w32_conv;       // [2*blocks][64 ic][9][64 oc]
     float* skip;                 // [CTAs][16 channel quads][512 rows][4] fp32 residual scratch (L2 resident)
+    int* overflow;               // set when an activation left the fp16 operand range (|x| > 6e4) and was clamped
     long long* dbg;              // optional timing probe (development): [64] clock64 stamps of CTA 0, first group
 };
 
@@ -490,6 +491,12 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
                         for (int qd = 0; qd < 4; qd++) {
                             o[qd * 4 + 0] += sk[qd].x; o[qd * 4 + 1] += sk[qd].y; o[qd * 4 + 2] += sk[qd].z; o[qd * 4 + 3] += sk[qd].w;
                         }
+                    }
+                    if (interior) {                                                 // fp16 operand range: never silent
+                        bool big = false;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) big |= !(o[j] <= 60000.0f);          // (also catches NaN)
+                        if (big) atomicOr(P.overflow, 1);
                     }
 #pragma unroll
                     for (int j = 0; j < 16; j++) o[j] = fminf(fmaxf(o[j], 0.0f), cap);   // ReLU

@@ -62,6 +62,8 @@ struct tg_engine {
     std::vector<Fetched> fetched; unsigned char* h_rec = nullptr; size_t h_rec_cap = 0; cudaEvent_t ev_rec = nullptr; bool rec_pending = false;
     int rec_row_bytes = 0;
     cudaEvent_t ev_x = nullptr;                  // cross-stream ordering with a caller's stream
+    int64_t sample_cap = 0, sample_count = 0;    // training samples emitted from the record ring
+    int* d_emit = nullptr; size_t d_emit_cap = 0;
     bool have_weights = false, have_zobrist = false;
     int64_t launches = 0;
     int n_eval_events = 2;
@@ -142,6 +144,7 @@ template <int BN> static int setup_kernel_attrs()
     CK(cudaFuncSetAttribute(k_reset<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_play<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_snapshot_roots<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_emit_samples<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_conv3x3_simt<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * (BN + 2) * (BN + 2) * 4));
     // the search kernels keep whole boards in shared memory: prefer the largest carve-out so that more games are resident
     CK(cudaFuncSetAttribute(k_root_begin<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -268,6 +271,11 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
         D.rec_moves = 2 * e->NN;
         DA(D.rec_move, rows); DA(D.rec_color, rows); DA(D.rec_k, rows); DA(D.rec_action, rows * e->AP); DA(D.rec_improved, rows * e->AP);
     }
+    if (cfg->sample_cap > 0) {
+        if (!cfg->record_ring) return bail(fail(TG_ERR_ARG, "sample_cap needs record_ring"));
+        e->sample_cap = cfg->sample_cap;
+        DA(D.smp_input, (size_t)cfg->sample_cap * e->PLANES); DA(D.smp_policy, (size_t)cfg->sample_cap * e->A); DA(D.smp_value, (size_t)cfg->sample_cap);
+    }
     {
         void* q = nullptr;
         if (cudaMalloc(&q, (size_t)games * 10) != cudaSuccess) return bail(fail(TG_ERR_CUDA, "reset staging"));
@@ -335,6 +343,20 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     return TG_OK;
 }
 
+// DualNet activations outside the fp16 operand range are clamped by the kernel AND reported: every entry point that returns
+// evaluator results to the host checks the flag (the stream is idle at these points) and fails loudly.
+static int check_net_overflow(tg_engine* e)
+{
+    if (!e->have_weights || !e->net.overflow || e->cfg.evaluator != TG_EVAL_DUALNET_TC) return 0;
+    int flag = 0;
+    CK(cudaMemcpy(&flag, e->net.overflow, 4, cudaMemcpyDeviceToHost));
+    if (!flag) return 0;
+    CK(cudaMemset(e->net.overflow, 0, 4));
+    return fail(TG_ERR_SEARCH, "DualNet activation overflow: a feature map left the fp16 operand range (|x| > 6e4) and was clamped; "
+                               "the tensor-core evaluator is specified for networks whose activations stay below that "
+                               "(use TG_EVAL_DUALNET_FP32 for others)");
+}
+
 static void free_net(tg_engine* e) { for (void* p : e->net_allocs) cudaFree(p); e->net_allocs.clear(); e->have_weights = false; }
 
 extern "C" void tg_engine_destroy(tg_engine* e)
@@ -351,6 +373,7 @@ extern "C" void tg_engine_destroy(tg_engine* e)
     if (e->h_visits) cudaFreeHost(e->h_visits);
     if (e->h_reset) cudaFreeHost(e->h_reset);
     if (e->h_rec) cudaFreeHost(e->h_rec);
+    if (e->d_emit) cudaFree(e->d_emit);
     for (cudaEvent_t ev : {e->ev_reset, e->ev_step, e->ev_rec, e->ev_x}) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -468,6 +491,11 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
         e->net_allocs.push_back(q);
         n.skip = reinterpret_cast<float*>(q);
         n.dbg = nullptr;
+        void* f = nullptr;
+        CK(cudaMalloc(&f, 4));
+        CK(cudaMemsetAsync(f, 0, 4, e->stream));
+        e->net_allocs.push_back(f);
+        n.overflow = reinterpret_cast<int*>(f);
     }
     CK(cudaStreamSynchronize(e->stream));
     e->have_weights = true;
@@ -712,9 +740,10 @@ extern "C" int tg_collect(tg_engine* e, tg_step_result* out)
         CK(cudaMemcpy(h, D.prof, sizeof h, cudaMemcpyDeviceToHost));
         CK(cudaMemset(D.prof, 0, 64 * sizeof(long long)));
         fprintf(stderr, "descend profile (game 0, cycles): copy %lld  select %lld (%lld)  put_stone %lld  expand %lld (%lld)  push_leaf %lld (%lld)"
-                        "  [select: scores %lld  argmax %lld  row wait %lld]\n",
-                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7], h[8], h[9], h[10]);
+                        "  [select: scores %lld  argmax %lld  row wait %lld  barrier after scores %lld]\n",
+                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7], h[8], h[9], h[10], h[11]);
     }
+    { const int orc = check_net_overflow(e); if (orc) return orc; }
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
     e->last_eval_ms = 0.f;
     for (int i = 2; i + 1 < e->n_eval_events; i += 2) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, e->events[i], e->events[i + 1])); e->last_eval_ms += ms; }
@@ -732,6 +761,7 @@ extern "C" int tg_collect(tg_engine* e, tg_step_result* out)
         if (out->resigned) out->resigned[g] = gs[GS_RESIGNED];
         if (out->score) { float f; memcpy(&f, &gs[GS_SCORE], 4); out->score[g] = f; }
         if (out->error) out->error[g] = gs[GS_ERROR];
+        if (out->n_moves) out->n_moves[g] = gs[GS_NMOVES];
     }
     e->last_eval_slots = uevals;
     if (out) {
@@ -783,6 +813,7 @@ extern "C" int tg_fetch_records(tg_engine* e, const int32_t* games_list, int32_t
     }
     if (total > e->h_rec_cap) {
         if (e->h_rec) cudaFreeHost(e->h_rec);
+    if (e->d_emit) cudaFree(e->d_emit);
         e->h_rec = nullptr; e->h_rec_cap = 0;
         const size_t want = std::max<size_t>(total + total / 2, (size_t)1 << 20);
         CK(cudaMallocHost(&e->h_rec, want));
@@ -955,7 +986,7 @@ extern "C" int tg_sync(tg_engine* e)
     if (!e) return fail(TG_ERR_ARG, "null engine");
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaStreamSynchronize(e->stream));
-    return TG_OK;
+    return check_net_overflow(e);
 }
 
 extern "C" int tg_forward(tg_engine* e, const float* planes, int32_t n, int32_t use_logit, float* policy, float* value)
@@ -976,7 +1007,7 @@ extern "C" int tg_forward(tg_engine* e, const float* planes, int32_t n, int32_t 
     CK(cudaEventRecord(e->events[1], e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
-    return TG_OK;
+    return check_net_overflow(e);
 }
 
 extern "C" int tg_tree_size(tg_engine* e, int32_t game, int32_t* num_nodes)
@@ -1007,6 +1038,93 @@ extern "C" int tg_read_node(tg_engine* e, int32_t game, int32_t index, tg_node_v
     CK(cudaStreamSynchronize(e->stream));
     o->num_children = hdr[H_K]; o->node_visits = hdr[H_NV]; o->virtual_loss = hdr[H_VL];
     memcpy(&o->node_value_sum, &hdr[H_VSUM], 4); memcpy(&o->raw_value, &hdr[H_RAW], 4);
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Training samples from the record ring
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t tg_emit_samples(tg_engine* e, const int32_t* games_list, int32_t n, const int32_t* plies, const int32_t* syms)
+{
+    if (!e || n < 0 || (n > 0 && (!games_list || !plies || !syms))) return fail(TG_ERR_ARG, "bad argument");
+    if (!e->sample_cap) return fail(TG_ERR_STATE, "engine was created without sample_cap");
+    if (e->step_pending) return fail(TG_ERR_STATE, "collect the step in flight first");
+    if (n == 0) return e->sample_count;
+    CK(cudaSetDevice(e->cfg.device));
+    std::vector<int> host((size_t)n * 18);                       // [games n | out_base n | plies 8n | syms 8n]
+    int64_t total = e->sample_count;
+    for (int i = 0; i < n; i++) {
+        const int g = games_list[i];
+        if (g < 0 || g >= e->cfg.games) return fail(TG_ERR_ARG, "game index out of range");
+        const int* gs = e->h_gs + (size_t)g * GS_STRIDE;         // state block of the last collected step
+        if (!gs[GS_FINISHED]) return fail(TG_ERR_STATE, "tg_emit_samples needs finished games (their slots are used as replay scratch)");
+        host[i] = g; host[(size_t)n + i] = (int)total;
+        int prev = -1, cnt = 0;
+        for (int j = 0; j < 8; j++) {
+            const int p = plies[(size_t)i * 8 + j], sy = syms[(size_t)i * 8 + j];
+            host[(size_t)2 * n + (size_t)i * 8 + j] = p; host[(size_t)10 * n + (size_t)i * 8 + j] = sy;
+            if (p < 0) continue;
+            if (p <= prev || p >= gs[GS_NMOVES] || cnt != j || sy < 0 || sy > 7) return fail(TG_ERR_ARG, "plies must be ascending move indices of the game, -1 padded at the end; syms in 0..7");
+            prev = p; cnt++;
+        }
+        total += cnt;
+    }
+    if (total > e->sample_cap) return fail(TG_ERR_STATE, "sample buffer full: read and clear it (tg_samples_read / tg_samples_clear)");
+    if (host.size() > e->d_emit_cap) {
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->d_emit) cudaFree(e->d_emit);
+        e->d_emit = nullptr; e->d_emit_cap = 0;
+        CK(cudaMalloc(&e->d_emit, host.size() * 2 * sizeof(int)));
+        e->d_emit_cap = host.size() * 2;
+    }
+    CK(cudaMemcpyAsync(e->d_emit, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));   // pageable source: staged before the call returns
+    const int* d = e->d_emit;
+    DISPATCH_N(e, (k_emit_samples<BN><<<(n + SEARCH_WARPS - 1) / SEARCH_WARPS, SEARCH_WARPS * 32, search_smem(BN), e->stream>>>(
+        e->D, d, n, d + (size_t)2 * n, d + (size_t)10 * n, d + n)));
+    e->launches++;
+    CK(cudaGetLastError());
+    e->sample_count = total;
+    return total;
+}
+
+extern "C" int tg_sample_buffers(tg_engine* e, float** input, double** policy, int32_t** value, int64_t* count, int64_t* cap)
+{
+    if (!e) return fail(TG_ERR_ARG, "null engine");
+    if (input) *input = e->D.smp_input;
+    if (policy) *policy = e->D.smp_policy;
+    if (value) *value = e->D.smp_value;
+    if (count) *count = e->sample_count;
+    if (cap) *cap = e->sample_cap;
+    return TG_OK;
+}
+
+double tg_round_3e(double x);                                    // tg_record.cpp: float(f"{x:.3e}")
+
+extern "C" int tg_samples_read(tg_engine* e, int64_t first, int64_t n, float* input, double* policy, int32_t* value, int32_t round_like_sgf)
+{
+    if (!e || first < 0 || n < 0 || first + n > e->sample_count) return fail(TG_ERR_ARG, "sample range outside [0, count)");
+    CK(cudaSetDevice(e->cfg.device));
+    if (input) CK(cudaMemcpyAsync(input, e->D.smp_input + (size_t)first * e->PLANES, (size_t)n * e->PLANES * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (policy) CK(cudaMemcpyAsync(policy, e->D.smp_policy + (size_t)first * e->A, (size_t)n * e->A * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (value) CK(cudaMemcpyAsync(value, e->D.smp_value + first, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (policy && round_like_sgf) {
+        // the reference's targets went through the SGF comment: four significant digits ("%.3e", selfplay_record.py:61) read
+        // back with float() (feature.py:96); unlisted points hold the literal 1e-18
+        const int64_t tot = n * e->A;
+        const int chunks = (int)std::min<int64_t>(64, std::max<int64_t>(1, tot / 4096));
+        parallel_for(chunks, [&](int c) {
+            const int64_t a = tot * c / chunks, b = tot * (c + 1) / chunks;
+            for (int64_t i = a; i < b; i++) if (policy[i] != 1e-18) policy[i] = tg_round_3e(policy[i]);
+        });
+    }
+    return TG_OK;
+}
+
+extern "C" int tg_samples_clear(tg_engine* e)
+{
+    if (!e) return fail(TG_ERR_ARG, "null engine");
+    e->sample_count = 0;
     return TG_OK;
 }
 

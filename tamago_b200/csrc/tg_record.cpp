@@ -64,6 +64,15 @@ static int fmt_3e(double x, char* out)
     return n;
 }
 
+// float(f"{x:.3e}"): the decimal round trip an improved-policy value takes through the SGF comment
+double tg_round_3e(double x)
+{
+    char buf[40];
+    const int n = fmt_3e(x, buf);
+    buf[n] = 0;
+    return strtod(buf, nullptr);
+}
+
 template <class TM, class TC, class TK>
 static void record_text(int n, int n_moves, const TM* moves, const TC* colors, const TK* num_children, const int16_t* action,
                         const double* improved, int stride, int winner, int resigned, double score, double komi, std::string& s)

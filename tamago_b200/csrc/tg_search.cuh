@@ -60,6 +60,10 @@ struct Dev {
     int16_t* rec_k;          // [games][rec_moves]      root.get_num_children()
     int16_t* rec_action;     // [games][rec_moves][AP]  root.action
     double* rec_improved;    // [games][rec_moves][AP]  root.calculate_improved_policy()
+    // training samples emitted straight from the record ring (nn/data_generator.py:89-149)
+    float* smp_input;        // [sample_cap][6][N*N]
+    double* smp_policy;      // [sample_cap][A]
+    int* smp_value;          // [sample_cap]
     // constants
     const u64* zob; const uint8_t* eye;
     long long* prof;         // optional clock64 accumulators of game 0 (development: TG_PROF=1)
@@ -708,6 +712,92 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_play(Dev D, const int16_t
     }
     wb_store<N>(sm.root, s, pool_of<N>(D), g, lane);
     if (lane == 0) gs[GS_COLOR] = color;
+}
+
+// Training samples of finished games straight from the device record ring: what
+// generate_reinforcement_learning_data (nn/data_generator.py:89-149) produces by re-reading the SGF -- the position before
+// each sampled ply as input planes under one of the 8 symmetries (nn/feature.py:10-57, go_board.py:74-104 sym_map), the
+// improved policy of that move's search as the target under the same symmetry with 1e-18 elsewhere (feature.py:80-102), and
+// the game result seen from the side to move (data_generator.py:121-137) -- without SGF text, parsing or a host replay.
+// One warp replays one game on a shared-memory board; which plies / symmetries are used is the caller's draw (the
+// reference takes them from numpy's global stream), passed as plies[8] (ascending, -1 padded) and syms[8].
+template <int N> __device__ __forceinline__ int sym_source(int idx, int sym)
+{   // raster index of the point that supplies output point idx (go_board.py:86-103)
+    const int x = idx % N, y = idx / N, m = N - 1;
+    int sx, sy;
+    switch (sym) {
+        case 1: sx = m - x; sy = y; break;
+        case 2: sx = x; sy = m - y; break;
+        case 3: sx = m - x; sy = m - y; break;
+        case 4: sx = y; sy = x; break;
+        case 5: sx = y; sy = m - x; break;
+        case 6: sx = m - y; sy = x; break;
+        case 7: sx = m - y; sy = m - x; break;
+        default: sx = x; sy = y; break;
+    }
+    return sy * N + sx;
+}
+
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_emit_samples(Dev D, const int* games, int n, const int* plies, const int* syms,
+                                                                    const int* out_base)
+{
+    using G = Geo<N>;
+    const int j = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    if (j >= n) return;
+    const int g = games[j];
+    WarpSmem<N>& sm = warp_smem<N>();
+    const int* gs = D.gs + (size_t)g * GS_STRIDE;
+    const int n_moves = min(gs[GS_NMOVES], D.rec_moves);
+    const int winner = gs[GS_WINNER];
+    int vlabel = winner == BLACK ? 2 : (winner == WHITE ? 0 : 1);             // sgf/reader.py:345-358 get_value_label
+    BScal s;
+    wb_clear<N>(sm.root, s, lane);
+    // the slot's history rows are free scratch: the game is over and tg_reset rewrites them for the next one
+    u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
+    int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
+    if (lane == 0) { hh[0] = 0; hp[0] = 0; }
+    __syncwarp();
+    const size_t r0 = (size_t)g * D.rec_moves;
+    int color = BLACK, next = 0, out = out_base[j];
+    for (int i = 0; i < n_moves && next < 8; i++) {
+        if (plies[j * 8 + next] == i) {
+            const int sym = syms[j * 8 + next];
+            float* pl = D.smp_input + (size_t)out * G::PLANES;
+            const int prev = hp[s.moves - 1];                                 // feature.py:34 record.get(moves - 1)
+            const bool prev_pass = s.moves > 1 && prev == PASS;               // :39
+            for (int idx = lane; idx < G::NN; idx += 32) {
+                const int src = sym_source<N>(idx, sym);
+                const int spos = onboard_pos<N>(src);
+                int d = sm.root.color[spos];
+                if (color == WHITE && d != 0) d = 3 - d;                      // :24-25
+                pl[idx] = d == 0 ? 1.0f : 0.0f; pl[G::NN + idx] = d == 1 ? 1.0f : 0.0f; pl[2 * G::NN + idx] = d == 2 ? 1.0f : 0.0f;
+                pl[3 * G::NN + idx] = (!prev_pass && prev == spos) ? 1.0f : 0.0f;   // :43-46
+                pl[4 * G::NN + idx] = prev_pass ? 1.0f : 0.0f;
+                pl[5 * G::NN + idx] = color == WHITE ? -1.0f : 1.0f;          // :50-52
+            }
+            // policy target: feature.py:91-100
+            const size_t rr = (r0 + i) * G::AP;
+            const int k = D.rec_k[r0 + i];
+            double p_pass = 1e-18;
+            for (int idx = lane; idx < G::NN; idx += 32) sm.s0[idx] = 1e-18;
+            __syncwarp();
+            for (int c = lane; c < k; c += 32) {
+                const int a = D.rec_action[rr + c];
+                if (a != PASS) sm.s0[(a / G::W - 1) * N + (a % G::W - 1)] = D.rec_improved[rr + c];
+            }
+            __syncwarp();
+            if (k > 0 && D.rec_action[rr + k - 1] == PASS) p_pass = D.rec_improved[rr + k - 1];     // PASS is the last child (tree.py:264)
+            double* po = D.smp_policy + (size_t)out * G::A;
+            for (int idx = lane; idx < G::NN; idx += 32) po[idx] = sm.s0[sym_source<N>(idx, sym)];
+            if (lane == 0) { po[G::NN] = p_pass; D.smp_value[out] = vlabel; }
+            __syncwarp();
+            out++; next++;
+        }
+        wb_put_stone<N>(sm.root, s, D.rec_move[r0 + i], color, D.zob, hh, hp, lane);   // data_generator.py:131
+        color = opp(color);
+        vlabel = 2 - vlabel;                                                  // :133
+    }
 }
 
 // Snapshot the root boards as leaf 0 of every game (used by the stand-alone feature-plane entry point).

@@ -19,7 +19,7 @@ def _ptr(a, ct):
 class Engine:
     def __init__(self, board_size=9, games=1, max_visits=400, komi=7.0, superko=True, batch_size=1, max_nodes=0,
                  device=0, evaluator=EVAL_DUALNET_TC, dedup=False, cgos_mode=False, net_blocks=6, seed=0,
-                 record_ring=False, scoring=0):
+                 record_ring=False, scoring=0, sample_cap=0):
         self.lib = _lib.load()
         self.n, self.games = board_size, games
         self.nn, self.A = board_size * board_size, board_size * board_size + 1
@@ -27,7 +27,7 @@ class Engine:
         self.stride = self.lib.tg_action_stride(board_size)
         self.komi, self.net_blocks, self.device = komi, net_blocks, device
         cfg = _lib.Config(board_size, komi, int(superko), games, max_visits, batch_size, max_nodes, device,
-                          evaluator, int(dedup), int(cgos_mode), net_blocks, seed, int(record_ring), int(scoring))
+                          evaluator, int(dedup), int(cgos_mode), net_blocks, seed, int(record_ring), int(sample_cap), int(scoring))
         h = C.c_void_p()
         check(self.lib.tg_engine_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -166,17 +166,58 @@ class Engine:
         full = getattr(self, "_pending_full", False)
         r = dict(move=np.zeros(g, np.int32), color=np.zeros(g, np.int32), num_children=np.zeros(g, np.int32),
                  finished=np.zeros(g, np.int32), winner=np.zeros(g, np.int32), resigned=np.zeros(g, np.int32),
-                 score=np.zeros(g, np.float32), error=np.zeros(g, np.int32), evals=np.zeros(2, np.int64))
+                 score=np.zeros(g, np.float32), error=np.zeros(g, np.int32), evals=np.zeros(2, np.int64),
+                 n_moves=np.zeros(g, np.int32))
         if full:
             r.update(action=np.zeros((g, s), np.int16), improved=np.zeros((g, s), np.float64), visits=np.zeros((g, s), np.int32))
         sr = _lib.StepResult()
         ct = dict(move=C.c_int32, color=C.c_int32, num_children=C.c_int32, action=C.c_int16, improved=C.c_double,
                   visits=C.c_int32, finished=C.c_int32, winner=C.c_int32, resigned=C.c_int32, score=C.c_float,
-                  error=C.c_int32, evals=C.c_int64)
+                  error=C.c_int32, evals=C.c_int64, n_moves=C.c_int32)
         for k, v in r.items():
             setattr(sr, k, _ptr(v, ct[k]))
         check(self.lib.tg_collect(self.h, C.byref(sr)))
         return r
+
+    # -- training samples straight from the record ring (nn/data_generator.py:89-149) -----------------------
+    def emit_samples(self, games, plies, syms):
+        """games [n], plies [n, 8] (ascending move indices, -1 padded), syms [n, 8] -> new sample count"""
+        gl = np.ascontiguousarray(games, dtype=np.int32)
+        pl = np.ascontiguousarray(plies, dtype=np.int32).reshape(len(gl), 8)
+        sy = np.ascontiguousarray(syms, dtype=np.int32).reshape(len(gl), 8)
+        return int(check(self.lib.tg_emit_samples(self.h, _ptr(gl, C.c_int32), len(gl), _ptr(pl, C.c_int32), _ptr(sy, C.c_int32))))
+
+    @property
+    def sample_count(self):
+        n, cap = C.c_int64(), C.c_int64()
+        check(self.lib.tg_sample_buffers(self.h, None, None, None, C.byref(n), C.byref(cap)))
+        return n.value
+
+    def read_samples(self, first=0, n=None, round_like_sgf=True):
+        """host copies: input [n, 6, N, N] f32, policy [n, N*N+1] f64, value [n] i32 (npz layout of data_generator.py:16-33)"""
+        n = self.sample_count - first if n is None else n
+        inp = np.zeros((n, 6, self.n, self.n), np.float32)
+        pol = np.zeros((n, self.A), np.float64)
+        val = np.zeros(n, np.int32)
+        check(self.lib.tg_samples_read(self.h, first, n, _ptr(inp, C.c_float), _ptr(pol, C.c_double), _ptr(val, C.c_int32), int(round_like_sgf)))
+        return inp, pol, val
+
+    def sample_tensors(self):
+        """torch views (zero copy) of the device-resident samples: input, policy (f64), value (i32), valid up to sample_count"""
+        import torch
+        pi, pp, pv, n, cap = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        check(self.lib.tg_sample_buffers(self.h, C.byref(pi), C.byref(pp), C.byref(pv), C.byref(n), C.byref(cap)))
+
+        class _View:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+        dev = torch.device("cuda", self.device)
+        k = max(1, n.value)
+        mk = lambda ptr, shape, ts: torch.as_tensor(_View(ptr.value, shape, ts), device=dev)
+        return (mk(pi, (k, 6, self.n, self.n), "<f4")[:n.value], mk(pp, (k, self.A), "<f8")[:n.value], mk(pv, (k,), "<i4")[:n.value])
+
+    def clear_samples(self):
+        check(self.lib.tg_samples_clear(self.h))
 
     # -- records of finished games (device ring -> SGF) ---------------------------------------------
     def fetch_records(self, games):
@@ -220,13 +261,14 @@ class Engine:
         g, s = self.games, self.stride
         r = dict(move=np.zeros(g, np.int32), color=np.zeros(g, np.int32), num_children=np.zeros(g, np.int32),
                  finished=np.zeros(g, np.int32), winner=np.zeros(g, np.int32), resigned=np.zeros(g, np.int32),
-                 score=np.zeros(g, np.float32), error=np.zeros(g, np.int32), evals=np.zeros(2, np.int64))
+                 score=np.zeros(g, np.float32), error=np.zeros(g, np.int32), evals=np.zeros(2, np.int64),
+                 n_moves=np.zeros(g, np.int32))
         if full:
             r.update(action=np.zeros((g, s), np.int16), improved=np.zeros((g, s), np.float64), visits=np.zeros((g, s), np.int32))
         sr = _lib.StepResult()
         ct = dict(move=C.c_int32, color=C.c_int32, num_children=C.c_int32, action=C.c_int16, improved=C.c_double,
                   visits=C.c_int32, finished=C.c_int32, winner=C.c_int32, resigned=C.c_int32, score=C.c_float,
-                  error=C.c_int32, evals=C.c_int64)
+                  error=C.c_int32, evals=C.c_int64, n_moves=C.c_int32)
         for k, v in r.items():
             setattr(sr, k, _ptr(v, ct[k]))
         check(self.lib.tg_genmove(self.h, mode, visits, int(strict), int(play), C.byref(sr)))

@@ -33,6 +33,34 @@ def symmetry_maps(n):
     return maps
 
 
+def draw_samples(n_moves):
+    """data_generator.py:123-124: the (plies, symmetries) one game contributes, drawn from numpy's global stream in the
+    reference's order.  Returns (plies[8] ascending, -1 padded; syms[8])."""
+    target_index = sorted(np.random.permutation(np.arange(n_moves))[:8])
+    sym_index_list = np.random.permutation(np.arange(8))
+    plies = np.full(8, -1, np.int32)
+    plies[:len(target_index)] = target_index
+    return plies, sym_index_list.astype(np.int32)
+
+
+def emit_from_ring(engine, finished_slots, n_moves):
+    """SURVEY 8f-1, the direct path: samples of the finished games go from the engine's device record ring to its
+    device-resident sample arrays (tg_emit_samples) -- no SGF text, no parser, no host replay, symmetry applied on the
+    device.  Call between collect() and the reset that recycles the slots.  Returns the new sample count."""
+    plies = np.zeros((len(finished_slots), 8), np.int32)
+    syms = np.zeros((len(finished_slots), 8), np.int32)
+    for j, nm in enumerate(n_moves):
+        plies[j], syms[j] = draw_samples(int(nm))
+    return engine.emit_samples(finished_slots, plies, syms)
+
+
+def save_samples_npz(engine, path, kifu_count, first=0, n=None):
+    """rl_data_<k>.npz (data_generator.py:16-33) from the device sample arrays, bit-equal to the SGF route"""
+    inp, pol, val = engine.read_samples(first, n, round_like_sgf=True)
+    np.savez_compressed(path, input=inp, policy=pol, value=val, kifu_count=np.array(kifu_count))
+    return len(val)
+
+
 def _rl_target(comment, n, perm):
     """generate_rl_target_data (feature.py:80-102): improved policy from the "k pos:prob ..." comment, 1e-18 elsewhere."""
     flat = np.full(n * n, 1e-18, np.float64)

@@ -28,13 +28,15 @@ class SelfPlayPool:
     after it has queued the NEXT engine step and written the files of the games that ended in the step it collected."""
 
     def __init__(self, save_dir, size, visits, games, indices, state_dict=None, device_index=0, dedup=True, seed=0,
-                 evaluator=EVAL_DUALNET_TC, zobrist=None, never_resign_fn=None, scoring=0):
+                 evaluator=EVAL_DUALNET_TC, zobrist=None, never_resign_fn=None, scoring=0, sample_cap=0, write_sgf=True):
         self.save_dir, self.size, self.visits, self.games = save_dir, size, visits, games
         self.indices = iter(indices)
         rng = random.Random(seed)
         self.nr = never_resign_fn or (lambda index: rng.randint(1, 10) == 1)                      # worker.py:53
         self.eng = Engine(board_size=size, games=games, max_visits=visits, komi=7.0, superko=True, device=device_index,
-                          evaluator=evaluator, dedup=dedup, seed=seed & 0xFFFFFFFFFFFFFFFF, record_ring=True, scoring=scoring)
+                          evaluator=evaluator, dedup=dedup, seed=seed & 0xFFFFFFFFFFFFFFFF, record_ring=True, scoring=scoring,
+                          sample_cap=sample_cap)
+        self.sample_cap, self.write_sgf, self.samples = sample_cap, write_sgf, 0
         if state_dict is not None:
             self.eng.load_state_dict(state_dict)
         if zobrist is not None:
@@ -44,6 +46,8 @@ class SelfPlayPool:
         self.active = np.zeros(games, bool)
         self.moves_played = self.files = self.file_moves = self.steps = 0
         self.in_flight = False
+        self.timing = dict(queue=0.0, wait=0.0, host_between_steps=0.0, write_files=0.0, fetch_records=0.0, emit_samples=0.0,
+                           refill_reset=0.0)             # host seconds by phase
 
     def _refill(self, slots):
         """next unplayed indices into these slots (worker.py:46-55); returns the slots that got a game"""
@@ -80,10 +84,14 @@ class SelfPlayPool:
 
     def step(self, queue_next=True):
         """Collect the step in flight (queue one first if there is none); returns (moves, games finished)."""
+        tm = self.timing
+        t0 = time.perf_counter()
         if not self.in_flight:
             self.queue()
         eng, active = self.eng, self.active
+        t1 = time.perf_counter()
         r = eng.collect()
+        t2 = time.perf_counter()
         self.in_flight = False
         self.last = r
         if (r["error"][active] != 0).any():
@@ -92,15 +100,27 @@ class SelfPlayPool:
         fin_slots = np.flatnonzero(active & (r["finished"] != 0))                                 # worker.py:76-90
         fin_index = self.slot_index[fin_slots].copy()
         if len(fin_slots):
-            eng.fetch_records(fin_slots)                     # copies are ordered before the reset below recycles the slots
+            ta = time.perf_counter()
+            if self.write_sgf:
+                eng.fetch_records(fin_slots)                 # copies are ordered before the reset below recycles the slots
+            tb_ = time.perf_counter()
+            if self.sample_cap:                              # training samples straight from the device ring
+                from ..nn.data_generator import emit_from_ring
+                self.samples = emit_from_ring(eng, fin_slots, r["n_moves"][fin_slots])
+            tc = time.perf_counter()
             self._refill(fin_slots)
+            tm["fetch_records"] += tb_ - ta; tm["emit_samples"] += tc - tb_; tm["refill_reset"] += time.perf_counter() - tc
         self.steps += 1
         self.moves_played += moves
+        t3 = time.perf_counter()
         if queue_next and active.any():
             self.queue()
-        if len(fin_slots):                                   # the GPU is already searching the next step
+        t4 = time.perf_counter()
+        if len(fin_slots) and self.write_sgf:                # the GPU is already searching the next step
             self.file_moves += eng.write_records(self.save_dir, fin_index)
             self.files += len(fin_slots)
+        t5 = time.perf_counter()
+        tm["queue"] += (t1 - t0) + (t4 - t3); tm["wait"] += t2 - t1; tm["host_between_steps"] += t3 - t2; tm["write_files"] += t5 - t4
         return moves, len(fin_slots)
 
     def close(self):
