@@ -202,6 +202,8 @@ int64_t tg_emit_samples(tg_engine* e, const int32_t* games, int32_t n, const int
 int     tg_sample_buffers(tg_engine* e, float** input, double** policy, int32_t** value, int64_t* count, int64_t* cap);
 int     tg_samples_read(tg_engine* e, int64_t first, int64_t n, float* input, double* policy, int32_t* value, int32_t round_like_sgf);
 int     tg_samples_clear(tg_engine* e);
+/* float(f"{p:.3e}") in place (sgf/selfplay_record.py:61 -> nn/feature.py:96), entries equal to 1e-18 untouched */
+void    tg_round_policy(double* p, int64_t n);
 
 /* instrumentation: kernels launched by this engine so far, and device milliseconds of the last tg_genmove */
 int64_t tg_launch_count(tg_engine* e);

@@ -73,6 +73,7 @@ EXPORTS = {
     "tg_sample_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), i64p, i64p]),
     "tg_samples_read": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, f32p, f64p, i32p, C.c_int32]),
     "tg_samples_clear": (C.c_int, [C.c_void_p]),
+    "tg_round_policy": (None, [f64p, C.c_int64]),
     "tg_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_stream_signal": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tg_tree_size": (C.c_int, [C.c_void_p, C.c_int32, i32p]),

@@ -815,7 +815,9 @@ extern "C" int tg_fetch_records(tg_engine* e, const int32_t* games_list, int32_t
         if (e->h_rec) cudaFreeHost(e->h_rec);
     if (e->d_emit) cudaFree(e->d_emit);
         e->h_rec = nullptr; e->h_rec_cap = 0;
-        const size_t want = std::max<size_t>(total + total / 2, (size_t)1 << 20);
+        // pinned allocations cost tens of milliseconds: size generously once (steady state: games / game length finish per
+        // step), double on the rare overflow (a pool whose games all end in the same step)
+        const size_t want = std::max<size_t>(2 * total, (size_t)32 << 20);
         CK(cudaMallocHost(&e->h_rec, want));
         e->h_rec_cap = want;
     }

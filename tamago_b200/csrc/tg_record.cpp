@@ -73,6 +73,12 @@ double tg_round_3e(double x)
     return strtod(buf, nullptr);
 }
 
+// the same for an array (entries equal to the literal 1e-18 default of nn/feature.py:90 are left alone)
+extern "C" void tg_round_policy(double* p, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) if (p[i] != 1e-18) p[i] = tg_round_3e(p[i]);
+}
+
 template <class TM, class TC, class TK>
 static void record_text(int n, int n_moves, const TM* moves, const TC* colors, const TK* num_children, const int16_t* action,
                         const double* improved, int stride, int winner, int resigned, double score, double komi, std::string& s)

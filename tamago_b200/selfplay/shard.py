@@ -68,3 +68,29 @@ def gather_training_arrays(arrays, dst=0):
         if rank == dst:
             out[key] = np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)])
     return out if rank == dst else None
+
+
+def gather_sample_tensors(tensors):
+    """north_star: "an optional NCCL gather collects finished npz records".  `tensors`: the device-resident sample arrays of
+    this rank (Engine.sample_tensors(): input f32 [n, 6, N, N], policy f64 [n, A], value i32 [n]); returns the same arrays
+    for ALL ranks' samples, in rank order, on every rank -- one all_gather of the counts and one padded all_gather per
+    array over NCCL (NVLink / NVSwitch), nothing touches the host."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tuple(t.clone() for t in tensors), [len(tensors[0])]
+    world = dist.get_world_size()
+    dev = tensors[0].device
+    n_local = torch.tensor([len(tensors[0])], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local)
+    counts = [int(c.item()) for c in counts]
+    nmax = max(counts + [1])
+    out = []
+    for t in tensors:
+        pad = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        pad[:len(t)] = t
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        out.append(torch.cat([p[:c] for p, c in zip(parts, counts)]))
+    return tuple(out), counts
