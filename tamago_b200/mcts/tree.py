@@ -105,13 +105,19 @@ class MCTSTree:
         """mcts/tree.py:57-105.  A non-empty analysis_query makes the search report like MCTSTree.search does (tree.py:155-174);
         the whole visit budget runs on the device in one call, so the report is written once, from the final tree."""
         visits = time_manager.get_num_visits_threshold(color)
+        if hasattr(time_manager, "start_timer"):
+            time_manager.start_timer()                                    # tree.py:71
         start = time.time()
         pos = self._run_puct(board, color, visits, self._is_strict(time_manager))
         root = self.get_root()
         if analysis_query and root.get_num_children() > 1:
             self._write_analysis(board, analysis_query)
-        if hasattr(time_manager, "set_search_speed"):
-            time_manager.set_search_speed(int(root.node_visits), time.time() - start)
+        if root.get_num_children() > 1:                                   # tree.py:76-77 returns before any bookkeeping
+            search_time = max(time.time() - start, 1e-9)
+            if hasattr(time_manager, "set_search_speed"):
+                time_manager.set_search_speed(int(root.node_visits), search_time)        # tree.py:94
+            if hasattr(time_manager, "substract_consumption_time"):
+                time_manager.substract_consumption_time(color, search_time)              # tree.py:95: TIME_CONTROL budgets shrink
         return pos
 
     def search(self, board, color, time_manager, analysis_query):
@@ -122,24 +128,30 @@ class MCTSTree:
             self._write_analysis(board, analysis_query)
 
     def ponder(self, board, color, analysis_query):
-        """mcts/tree.py:108-127: search until input arrives on stdin.  The device search runs fixed budgets, so pondering
-        re-searches with a doubling budget (every round restarts the tree) and reports after each round."""
-        from .time_manager import TimeManager, TimeControl
-        visits, cap = 256, int(analysis_query.get("max_visits", 65536))
-        while True:
-            tm = TimeManager(TimeControl.STRICT_PLAYOUT, constant_visits=visits)
-            self._run_puct(board, color, visits, True)
+        """mcts/tree.py:108-127: search without a visit limit until input arrives on stdin (gtp/client.py lz-analyze).  The
+        device search runs fixed budgets, so pondering re-searches with a doubling budget (every round restarts the tree)
+        and reports after each round.  It stops when stdin has input, when the budget reaches analysis_query["max_visits"]
+        (default: the visits the device tree can hold, 65536 like MCTS_TREE_SIZE), or -- when the caller did not ask for
+        stdin polling with the "ponder" flag -- after ONE round of analysis_query.get("visits", 1024) visits."""
+        cap = int(analysis_query.get("max_visits", 65536))
+        if not analysis_query.get("ponder", False):
+            self._run_puct(board, color, min(cap, int(analysis_query.get("visits", 1024))), True)
             if analysis_query:
                 self._write_analysis(board, analysis_query)
+            return
+        visits = min(cap, 256)
+        self._get_engine(board, cap)                                      # one engine sized for the largest round
+        while True:
+            self._run_puct(board, color, visits, True)
+            self._write_analysis(board, analysis_query)
             if visits >= cap:
                 break
-            if analysis_query.get("ponder", False):
-                try:
-                    rlist, _, _ = select.select([sys.stdin], [], [], 0)
-                except (ValueError, OSError):
-                    rlist = [True]
-                if rlist:
-                    break
+            try:
+                rlist, _, _ = select.select([sys.stdin], [], [], 0)
+            except (ValueError, OSError):
+                rlist = [True]
+            if rlist:
+                break
             visits = min(cap, visits * 2)
 
     def search_with_callback(self, board, color, callback):

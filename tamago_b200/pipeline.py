@@ -97,7 +97,8 @@ def run_iteration(program_dir, size=9, visits=16, num_data=10000, batch_size=256
     tr = train_with_gumbel_alphazero_on_gpu(program_dir, size, batch_size, device=torch.device("cuda", dev), amp=amp, max_steps=max_train_steps)
     torch.cuda.synchronize(dev)
     out["train_seconds"] = time.perf_counter() - t2
-    out.update(moves=moves, games=len(mine), num_trained_batches=tr["num_trained_batches"], allreduce_bytes_per_step=tr["allreduce_bytes_per_step"])
+    out.update(moves=moves, games=len(mine), num_trained_batches=tr["num_trained_batches"], allreduce_bytes_per_step=tr["allreduce_bytes_per_step"],
+               net=tr["net"])
     return out
 
 
@@ -120,7 +121,7 @@ def main():
     for it in range(a.iterations):
         r = run_iteration(a.program_dir, a.size, a.visits, a.num_data, pool_size=a.pool_size, data=a.data, scoring=a.scoring)
         if _dist()[0] == 0:
-            print(json.dumps(r))
+            print(json.dumps({k: v for k, v in r.items() if k != "net"}))
     if dist.is_initialized():
         dist.destroy_process_group()
 
