@@ -184,7 +184,7 @@ def run_reference(a, out=sys.stdout):
         return
     cores = host_cores()
     # bounded sample: the whole run (start-up + warm + K windows) stays within ~3 minutes whatever K the driver asks for
-    step_s = float(min(20.0, max(4.0, 150.0 / max(1, a.steps))))
+    step_s = a.ref_step_seconds if a.ref_step_seconds > 0 else float(min(20.0, max(4.0, 150.0 / max(1, a.steps))))
     warm_s = 8.0 + 4.0 * min(a.warmup, 2)
     res = reference_run("sh", a.size, a.visits, cores, warm_s, a.steps, step_s) if not a.ref_port else None
     if res is not None:
@@ -451,6 +451,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="window of the bounded cpu_baseline sample of the reference")
     ap.add_argument("--cpu-moves", type=int, default=12, help="moves of the bounded cpu_baseline sample of the port")
     ap.add_argument("--ref-moves", type=int, default=6, help="moves per process and step of the port fallback in the --impl reference arm")
+    ap.add_argument("--ref-step-seconds", type=float, default=0.0, help="--impl reference: seconds per step window (0 = sized so that the run takes ~3 minutes)")
     ap.add_argument("--ref-port", type=int, default=0, help="--impl reference: time the oracle port even when baseline/_ref exists")
     a = ap.parse_args()
     # stdout carries exactly one JSON line: anything libraries write to fd 1 meanwhile (e.g. the NCCL version banner) goes to stderr

@@ -214,6 +214,9 @@ def train_with_gumbel_alphazero_on_gpu(program_dir, board_size, batch_size, devi
         if rank == 0:
             print(f"load {model_file_path}")
         net.load_state_dict(torch.load(model_file_path, map_location=device))
+    if world > 1:                                                   # every rank trains the same network: rank 0's initialisation
+        for t in list(net.parameters()) + list(net.buffers()):
+            dist.broadcast(t.data, 0)
     state_file_path = os.path.join(program_dir, "model", "rl-state.ckpt")
     if os.path.exists(state_file_path):
         if rank == 0:
