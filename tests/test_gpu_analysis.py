@@ -78,8 +78,13 @@ def test_search_and_ponder_report(golden_dir, capsys):
     assert rep["visits"] == tree.get_root().node_visits and rep["visits"] >= 199
     assert sum(m["visits"] for m in rep["moves"]) == rep["visits"] and rep["moves"][0]["order"] == 0
     assert all(m["pv"].split(" ")[0] == m["move"] for m in rep["moves"])
-    tree.ponder(board, Stone.BLACK, {"mode": "lz", "interval": 100, "max_visits": 512})
+    # without the "ponder" flag (no stdin polling) the analysis is ONE bounded round (it used to keep doubling)
+    tree.ponder(board, Stone.BLACK, {"mode": "lz", "interval": 100, "visits": 300})
     lines = capsys.readouterr().out.strip().split("\n")
-    assert len(lines) == 2 and all(l.startswith("info move ") for l in lines)      # 256- and 512-visit rounds
+    assert len(lines) == 1 and lines[0].startswith("info move ") and tree.get_root().node_visits == 300
+    # with it, rounds double until stdin has input or max_visits is reached (pytest's captured stdin ends it after a round)
+    tree.ponder(board, Stone.BLACK, {"mode": "lz", "interval": 100, "ponder": True, "max_visits": 512})
+    lines = capsys.readouterr().out.strip().split("\n")
+    assert 1 <= len(lines) <= 2 and all(l.startswith("info move ") for l in lines)
     with pytest.raises(NotImplementedError):
         tree.search_with_callback(board, Stone.BLACK, lambda path: True)
