@@ -654,19 +654,36 @@ __global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit)
                 t.cpol[(size_t)ni[u] * G::AP + c[u]] = (double)p;
             }
     }
+    // (b) tree.py:301-313 + node.py:118-138.  What the sequential walk needs from each leaf (backed-up value, path length,
+    //     the last 32 path entries) is fetched by the whole block first, so the walk itself only pays the node-pool updates.
+    extern __shared__ __align__(16) unsigned char bk_smem[];
+    constexpr int BK_MAX = 256;
+    float* s_val = reinterpret_cast<float*>(bk_smem);                            // [BK_MAX]
+    int* s_plen = reinterpret_cast<int*>(bk_smem + BK_MAX * 4);                  // [BK_MAX]
+    unsigned* s_path = reinterpret_cast<unsigned*>(bk_smem + BK_MAX * 8);        // [BK_MAX][32]
+    const bool staged = nl <= BK_MAX;
+    if (staged) {
+        for (int i = tid; i < nl; i += NT) {
+            const float* v = D.value + (size_t)(slot0 + D.leaf_slot[q + i]) * 3;
+            s_val[i] = __fadd_rn(v[0], __fmul_rn(v[1], 0.5f));                                                        // :303
+            s_plen[i] = D.path_len[q + i];
+        }
+        for (int p = tid; p < nl * 32; p += NT) {
+            const int i = p >> 5, d = p & 31, plen = D.path_len[q + i];
+            s_path[p] = d < plen ? D.path[(q + i) * D.max_depth + plen - 1 - d] : 0u;
+        }
+    }
+    __syncthreads();
     if (warp != 0) return;
-    // (b) tree.py:301-313 + node.py:118-138
-    auto leaf_head = [&](int i, float& val0, int& plen, unsigned& e0) {
-        const float* v = D.value + (size_t)(slot0 + D.leaf_slot[q + i]) * 3;
-        val0 = __fadd_rn(v[0], __fmul_rn(v[1], 0.5f));                                                                // :303
-        plen = D.path_len[q + i];
-        e0 = lane < plen ? D.path[(q + i) * D.max_depth + plen - 1 - lane] : 0u;
-    };
-    float val0n = 0.f; int plenn = 0; unsigned en = 0;
-    leaf_head(0, val0n, plenn, en);
     for (int i = 0; i < nl; i++) {
-        const float val0 = val0n; const int plen = plenn; const unsigned e0 = en;
-        if (i + 1 < nl) leaf_head(i + 1, val0n, plenn, en);                      // next leaf's loads overlap this leaf's updates
+        float val0; int plen; unsigned e0;
+        if (staged) { val0 = s_val[i]; plen = s_plen[i]; e0 = s_path[i * 32 + lane]; }
+        else {
+            const float* v = D.value + (size_t)(slot0 + D.leaf_slot[q + i]) * 3;
+            val0 = __fadd_rn(v[0], __fmul_rn(v[1], 0.5f));
+            plen = D.path_len[q + i];
+            e0 = lane < plen ? D.path[(q + i) * D.max_depth + plen - 1 - lane] : 0u;
+        }
         if (plen > 0) {
             const unsigned* path = D.path + (q + i) * D.max_depth;
             const float val1 = __fsub_rn(1.0f, val0), val2 = __fsub_rn(1.0f, val1);

@@ -695,11 +695,11 @@ extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int3
                     } else if (games <= e->sms) {        // block-per-game, 512 threads per ply (tg_block.cuh): single-game genmove
                         k_descend_puct_blk<BN, 512><<<games, 512, sizeof(BlkSmem<BN, 512>), e->stream>>>(D, e->eye2, visits, batch, strict);
                         rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
-                        k_backup_blk<BN, 512><<<games, 512, 0, e->stream>>>(D, 0);
+                        k_backup_blk<BN, 512><<<games, 512, 256 * 136, e->stream>>>(D, 0);
                     } else {                             // block-per-game, 256 threads: up to three CTAs per SM
                         k_descend_puct_blk<BN, 256><<<games, 256, sizeof(BlkSmem<BN, 256>), e->stream>>>(D, e->eye2, visits, batch, strict);
                         rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
-                        k_backup_blk<BN, 256><<<games, 256, 0, e->stream>>>(D, 0);
+                        k_backup_blk<BN, 256><<<games, 256, 256 * 136, e->stream>>>(D, 0);
                     }
                     e->launches += 2;
                 }
