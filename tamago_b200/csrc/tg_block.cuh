@@ -325,7 +325,14 @@ __device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const typename BlkSmem
         const int cv = st.vis[i] + st.vl[i];
         const double num = dmul(dmul(1.0, st.pol[i]), sq);
         double v = num;
-        if (cv != 0) v = dadd(ddiv((double)st.vsum[i], (double)cv), ddiv(num, (double)(cv + 1)));
+        if (cv != 0) {
+            // a zero numerator (an edge with virtual losses but no finished visit yet: value sum 0; a prior that underflowed)
+            // sends the correctly rounded division down its slow path (~10x the cycles); 0 / x = +0 exactly, so skip it
+            const float vs = st.vsum[i];
+            const double q = vs == 0.0f ? 0.0 : ddiv((double)vs, (double)cv);
+            const double u = num == 0.0 ? 0.0 : ddiv(num, (double)(cv + 1));
+            v = dadd(q, u);
+        }
         if (cgos && i == nk - 1) v = dsub(v, 0.1);
         if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
     }

@@ -76,6 +76,7 @@ template <int N> struct WarpSmem {
     alignas(16) double s0[Geo<N>::AP];
     double s1[Geo<N>::AP];
     int16_t memo[Geo<N>::AP];        // sequential halving: root child -> first leaf of this phase that went through it
+    alignas(16) int sthdr[H_STRIDE]; // PUCT: staged node header
 };
 
 template <int N> __device__ __forceinline__ BoardPool<N> pool_of(const Dev& D)
@@ -311,6 +312,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_sh(Dev D)
 
 // Up to `batch` descents of search_mcts (tree.py:199-244) with the early stop of TimeManager.is_move_decided
 // (time_manager.py:146-163) checked after every descent as in MCTSTree.search (tree.py:146-152).
+//   Every ply reads its node from shared memory: the rows are staged with one burst of asynchronous copies that is issued
+//   as soon as the node is known -- the root's at kernel start (under the board load) and at the end of a descent, a
+//   child's right after the selection that leads to it (under put_stone).
 template <int N>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int visits, int batch, int strict)
 {
@@ -322,9 +326,15 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
     __syncwarp();
     if (!gs[GS_ACTIVE] || gs[GS_FINISHED] || gs[GS_ERROR] || gs[GS_DONE]) return;
     WarpSmem<N>& sm = warp_smem<N>();
+    static_assert(sizeof(WAnalysis<N>) >= 4 * G::AP * 4 + G::AP * 2, "child-row staging aliases the analysis scratch");
+    // staging lives in the expansion scratch (never live at the same time: a descent expands only at its last ply)
+    const SelStage stage = { sm.s0, reinterpret_cast<int*>(&sm.an), reinterpret_cast<int*>(&sm.an) + G::AP,
+                             reinterpret_cast<float*>(&sm.an) + 2 * G::AP, reinterpret_cast<int*>(&sm.an) + 3 * G::AP,
+                             reinterpret_cast<int16_t*>(reinterpret_cast<int*>(&sm.an) + 4 * G::AP), sm.sthdr };
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    stage_node_warp<G::AP>(stage, t, 0, lane);                                    // root rows arrive under the board load
     BScal rs;
     wb_load<N>(sm.root, rs, pool_of<N>(D), g, lane);
-    const Tree t = tree_of<G::AP>(D.tree, g);
     const int root_color = gs[GS_COLOR];
     u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
     int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
@@ -332,19 +342,21 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
     for (int b = 0; b < batch; b++) {
         int desc = gs[GS_DESC];
         if (desc >= visits) { if (lane == 0) gs[GS_DONE] = 1; __syncwarp(); break; }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
         if (desc > 0) {
             // is_move_decided (time_manager.py:146-163), evaluated after the previous descent and after the
             // mini-batch flush that descent may have triggered (tree.py:149-152, 240-241):
             // sorted(children_visits)[-1] - [-2] against the remaining budget
-            const int k = t.hdr[H_K];
+            const int k = stage.hdr[H_K];
             int top1 = 0;
-            for (int i = lane; i < k; i += 32) top1 = max(top1, t.cvis[i]);
+            for (int i = lane; i < k; i += 32) top1 = max(top1, stage.vis[i]);
             top1 = warp_max_i(top1);
             int nmax = 0, top2 = 0;
-            for (int i = lane; i < k; i += 32) { const int v = t.cvis[i]; if (v == top1) nmax++; else top2 = max(top2, v); }
+            for (int i = lane; i < k; i += 32) { const int v = stage.vis[i]; if (v == top1) nmax++; else top2 = max(top2, v); }
             nmax = warp_sum_i(nmax); top2 = warp_max_i(top2);
             if (nmax >= 2) top2 = top1;
-            const int remaining = visits - t.hdr[H_NV];
+            const int remaining = visits - stage.hdr[H_NV];
             const int cutoff = strict ? 0 : top1 - top2;
             if (remaining < cutoff) { if (lane == 0) gs[GS_DONE] = 1; __syncwarp(); break; }
         }
@@ -357,41 +369,49 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
         unsigned* path = D.path + ((size_t)g * D.cap + gs[GS_NLEAF]) * D.max_depth;
         bool fail = false;
         for (;;) {
-            static_assert(sizeof(WAnalysis<N>) >= 3 * G::AP * 4, "child-row staging aliases the analysis scratch");
-            const SelStage stage = { sm.s0, reinterpret_cast<int*>(&sm.an), reinterpret_cast<int*>(&sm.an) + G::AP,
-                                     reinterpret_cast<float*>(&sm.an) + 2 * G::AP };
-            const int next = select_puct<G::AP>(t, cur, D.cgos != 0, lane, stage);      // :213
+            const int next = select_puct(stage, D.cgos != 0, lane);                     // :213
             if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
             const size_t row = (size_t)cur * G::AP;
-            const int mv = t.action[row + next];
-            if (lane == 0) path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+            const int mv = stage.action[next];
+            const int cv_before = stage.vis[next] + stage.vl[next];
+            int ci = stage.cidx[next];
+            const int vl_node = stage.hdr[H_VL], vl_edge = stage.vl[next];
+            __syncwarp();                                                        // every lane has read the staged node
+            // the child's rows are needed next unless this edge ends the descent: fetch them under put_stone
+            const bool spec = ci != NOT_EXPANDED && cv_before >= 1;
+            if (spec) stage_node_warp<G::AP>(stage, t, ci, lane);
+            if (lane == 0) {
+                path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+                t.hdr[(size_t)cur * H_STRIDE + H_VL] = vl_node + 1; t.cvl[row + next] = vl_edge + 1;       // :221 add_virtual_loss
+            }
             plen++;
             wb_put_stone<N>(sm.scratch, s, mv, color, D.zob, hh, hp, lane);      // :217
             if (prof) { const long long c = clock64(); D.prof[2] += c - pt0; pt0 = c; }
             color = opp(color);
-            if (lane == 0) { t.hdr[(size_t)cur * H_STRIDE + H_VL] += 1; t.cvl[row + next] += 1; }      // :221
-            __syncwarp();
             int expand_threshold = 1;
             if (s.moves > 2) {                                                   // :224-229
                 if (s.moves - 1 >= G::MAXREC) { if (lane == 0) gs[GS_ERROR] |= ERR_HISTORY; fail = true; break; }
                 if (hp[s.moves - 1] == PASS && hp[s.moves - 2] == PASS) expand_threshold = 10000000;
             }
-            if (t.cvis[row + next] + t.cvl[row + next] < expand_threshold + 1) { // :231-241
-                int ci = t.cidx[row + next];
+            if (cv_before + 1 < expand_threshold + 1) {                          // :231-241
+                if (spec) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); }   // two-pass rule: drain the unused fetch
                 if (ci == NOT_EXPANDED) {
                     if (prof) pt0 = clock64();
                     ci = expand_node<N>(D, t, g, gs, sm.scratch, sm.an, s, color, hh, move_key, lane);
                     if (prof) { const long long c = clock64(); D.prof[3] += c - pt0; pt0 = c; D.prof[6]++; }
                     if (ci < 0) { fail = true; break; }
                     if (lane == 0) t.cidx[row + next] = ci;
+                    __threadfence_block();
                     __syncwarp();
                 }
+                // the expansion scratch is free again: the root's rows for the next descent arrive under push_leaf
+                if (b + 1 < batch) stage_node_warp<G::AP>(stage, t, 0, lane);
                 if (prof) pt0 = clock64();
                 push_leaf<N>(D, g, gs, sm.scratch, s, color, path, plen, ci, lane, -1, true);
                 if (prof) { const long long c = clock64(); D.prof[4] += c - pt0; pt0 = c; D.prof[7]++; }
                 break;
             }
-            cur = t.cidx[row + next];
+            cur = ci;
             if (plen >= D.max_depth) { if (lane == 0) gs[GS_ERROR] |= ERR_DEPTH; fail = true; break; }
         }
         __syncwarp();
@@ -399,6 +419,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
         if (lane == 0) gs[GS_DESC] = desc + 1;
         __syncwarp();
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -49,32 +49,39 @@ template <int AP> __device__ __forceinline__ Tree tree_of(const TreePool& p, int
 }
 
 // Shared-memory staging of one node's child rows for the PUCT selection ("child visit/value stats staged in shared memory").
-struct SelStage { double* pol; int* vis; int* vl; float* vsum; };
+// Everything a ply reads from the node -- visits, virtual losses, value sums, priors, child indices, actions and the node
+// header -- is fetched with ONE burst of 16-byte asynchronous copies; the descent issues the burst for the next node as
+// soon as it knows it (right after the selection, under put_stone), so the L2 latency of a ply is hidden.
+struct SelStage { double* pol; int* vis; int* vl; float* vsum; int* cidx; int16_t* action; int* hdr; };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-// node.py:141-157 + pucb.py:8-29.  Returns the child index (warp-uniform).
-//   The child rows live in the HBM/L2 node pool.  All four rows are fetched with one burst of 16-byte asynchronous copies
-//   (one memory latency per selection instead of one per 32-child sweep); the float64 arithmetic then runs from shared
-//   memory in the reference's order (lowest index first on ties).
 template <int AP>
-__device__ inline int select_puct(const Tree& t, int node, bool cgos, int lane, const SelStage& st)
+__device__ __forceinline__ void stage_node_warp(const SelStage& st, const Tree& t, int node, int lane)
 {
     const size_t row = (size_t)node * AP;
     for (int c = lane; c < AP / 4; c += 32) {
         cp_async16(st.vis + 4 * c, t.cvis + row + 4 * c);
         cp_async16(st.vl + 4 * c, t.cvl + row + 4 * c);
         cp_async16(st.vsum + 4 * c, t.cvsum + row + 4 * c);
+        cp_async16(st.cidx + 4 * c, t.cidx + row + 4 * c);
     }
     for (int c = lane; c < AP / 2; c += 32) cp_async16(st.pol + 2 * c, t.cpol + row + 2 * c);
-    const int* h = t.hdr + (size_t)node * H_STRIDE;
-    const int k = h[H_K];
-    const double sq = sqrt((double)(h[H_NV] + h[H_VL] + 1));
+    for (int c = lane; c < AP / 8; c += 32) cp_async16(st.action + 8 * c, t.action + row + 8 * c);
+    if (lane < H_STRIDE / 4) cp_async16(st.hdr + 4 * lane, t.hdr + (size_t)node * H_STRIDE + 4 * lane);
+}
+
+// node.py:141-157 + pucb.py:8-29 on a staged node.  Returns the child index (warp-uniform); the float64 arithmetic runs in
+// the reference's order (lowest index first on ties).
+__device__ inline int select_puct(const SelStage& st, bool cgos, int lane)
+{
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
+    const int k = st.hdr[H_K];
+    const double sq = sqrt((double)(st.hdr[H_NV] + st.hdr[H_VL] + 1));
     double bv = 0.0; int bi = 0x7fffffff;
     for (int i = lane; i < k; i += 32) {          // (unrolling for overlapping divisions was measured slower: 7.4 k -> 10.6 k cycles)
         const int cv = st.vis[i] + st.vl[i];
@@ -83,7 +90,14 @@ __device__ inline int select_puct(const Tree& t, int node, bool cgos, int lane, 
         // wide node skip them altogether)
         const double num = dmul(dmul(1.0, st.pol[i]), sq);
         double v = num;
-        if (cv != 0) v = dadd(ddiv((double)st.vsum[i], (double)cv), ddiv(num, (double)(cv + 1)));
+        if (cv != 0) {
+            // zero numerators (virtual losses without a finished visit; an underflowed prior) would take the division's slow
+            // path; 0 / x = +0 exactly
+            const float vs = st.vsum[i];
+            const double q = vs == 0.0f ? 0.0 : ddiv((double)vs, (double)cv);
+            const double u = num == 0.0 ? 0.0 : ddiv(num, (double)(cv + 1));
+            v = dadd(q, u);
+        }
         if (cgos && i == k - 1) v = dsub(v, 0.1);
         if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
     }
