@@ -89,26 +89,15 @@ __device__ __forceinline__ void blk_sum_max(BlkSmem<N, NT>& sm, Blk<NT>& k, int&
     for (int w = 0; w < NT / 32; w++) { ss += sm.r_i[p][w]; mm = max(mm, sm.r_j[p][w]); }
     s = ss; mx = mm;
 }
-// argmax with numpy semantics (first index wins ties); idx = INT_MAX marks an empty thread.
-//   Doubles are mapped to order-preserving 64-bit integer keys, so the warp stage is three REDUX instructions (max of the
-//   high words, max of the low words among the holders of that maximum, min of the indices among the holders of both)
-//   instead of a five-round shuffle butterfly on (double, index) pairs -- measured 2.5 k -> see profiles/r02_puct_block.md.
-__device__ __forceinline__ u64 order_key(double v)
-{
-    const u64 b = (u64)__double_as_longlong(v == 0.0 ? 0.0 : v);              // -0.0 and +0.0 compare equal
-    return b ^ ((u64)((long long)b >> 63) | 0x8000000000000000ull);
-}
+// argmax with numpy semantics (first index wins ties); idx = INT_MAX marks an empty thread.  Warp stage: three REDUX
+// instructions on order-preserving integer keys (tg_common.cuh warp_argmax_key); block stage: one slot per warp.
 template <int N, int NT>
 __device__ __forceinline__ int blk_argmax_d(BlkSmem<N, NT>& sm, Blk<NT>& k, double v, int idx)
 {
-    const bool have = idx != 0x7fffffff;
-    const u64 key = have ? order_key(v) : 0ull;                               // real keys are never 0 (no NaNs in the scores)
-    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
-    const unsigned mi = __reduce_min_sync(0xffffffffu, (have && hi == mhi && lo == mlo) ? (unsigned)idx : 0x7fffffffu);
+    u64 key = idx != 0x7fffffff ? order_key(v) : 0ull;
+    warp_argmax_key(key, idx);
     const int p = k.ph; k.ph ^= 1;
-    if (k.lane == 0) { sm.r_x[p][k.warp] = ((u64)mhi << 32) | mlo; sm.r_i[p][k.warp] = (int)mi; }
+    if (k.lane == 0) { sm.r_x[p][k.warp] = key; sm.r_i[p][k.warp] = idx; }
     k.sync();
     u64 bk = sm.r_x[p][0]; int bi = sm.r_i[p][0];
 #pragma unroll

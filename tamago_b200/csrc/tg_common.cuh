@@ -78,14 +78,27 @@ __device__ __forceinline__ u64 shfl_u64(u64 v, int src)
 }
 
 // argmax with numpy semantics (first index wins ties): lanes hold (value, index), index = INT_MAX when empty.
+//   Doubles are mapped to order-preserving 64-bit integer keys, so the reduction is three REDUX instructions (max of the
+//   high words, max of the low words among the holders of that maximum, min of the indices among the holders of both)
+//   instead of a five-round shuffle butterfly on (double, index) pairs.  Scores are never NaN; -0.0 is folded into +0.0.
+__device__ __forceinline__ u64 order_key(double v)
+{
+    const u64 b = (u64)__double_as_longlong(v == 0.0 ? 0.0 : v);
+    return b ^ ((u64)((long long)b >> 63) | 0x8000000000000000ull);
+}
+__device__ __forceinline__ void warp_argmax_key(u64& key, int& idx)
+{   // key = 0 marks an empty lane (real keys are never 0)
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const unsigned mi = __reduce_min_sync(0xffffffffu, (key != 0ull && hi == mhi && lo == mlo) ? (unsigned)idx : 0x7fffffffu);
+    key = ((u64)mhi << 32) | mlo; idx = (int)mi;
+}
 __device__ __forceinline__ void warp_argmax_d(double& v, int& idx)
 {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        double ov = shfl_xor_d(v, o);
-        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (oi != 0x7fffffff && (idx == 0x7fffffff || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
-    }
+    u64 key = idx != 0x7fffffff ? order_key(v) : 0ull;
+    warp_argmax_key(key, idx);
+    // (callers only use idx; v is left as this lane's own value)
 }
 
 }  // namespace tg
