@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libtamago_b200.so")
 SOURCES = ["tg_engine.cu", "tg_record.cpp"]
 HEADERS = ["tg_common.cuh", "tg_detmath.cuh", "tg_board.cuh", "tg_tree.cuh", "tg_search.cuh", "tg_block.cuh", "tg_dualnet.cuh",
            os.path.join("..", "..", "include", "tamago_b200.h")]
-NVCC_FLAGS = (["-DTG_PROF_FINE"] if os.environ.get("TG_PROF_FINE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               # search math must round like numpy/torch scalar arithmetic: no FMA contraction (the DualNet
               # kernels use explicit fmaf where they want it)
               "-fmad=false", "--expt-relaxed-constexpr", "--extended-lambda",

@@ -33,6 +33,7 @@ template <int N, int NT> struct BlkSmem {
         alignas(16) int hdr[H_STRIDE];
     } st[2];
     alignas(16) uint32_t eye2[4096];                       // eye table, two bits per 3x3 code (pattern.py:53-98)
+    alignas(16) u64 zob[4 * G::CP];                        // Zobrist keys (zobrist_hash.py:9-10): every put_stone reads one
     WBoard<N> root;
     WBoard<N> scratch;
     alignas(16) WAnalysis<N> an;                           // expansion scratch
@@ -52,73 +53,68 @@ template <int NT> struct Blk {
     __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 
-// ---- block reductions: warp shuffle, one shared slot per warp, every thread folds the NW slots -------------------
+// ---- block reductions: REDUX / shuffle inside a warp, one shared slot per warp, then EVERY warp folds the NW slots with
+// its lanes in parallel (lane l reads slot l, one more REDUX) -- no second barrier, and no 16-step serial fold per thread
+// (with 512 threads the redundant serial folds of 16 warps on 4 schedulers were the larger part of a selection).
 template <int N, int NT>
 __device__ __forceinline__ void blk_xor_sum(BlkSmem<N, NT>& sm, Blk<NT>& k, u64& x, int& cnt)
 {
+    constexpr int NW = NT / 32;
     x = warp_xor64(x); cnt = warp_sum_i(cnt);
     const int p = k.ph; k.ph ^= 1;
     if (k.lane == 0) { sm.r_x[p][k.warp] = x; sm.r_i[p][k.warp] = cnt; }
     k.sync();
-    u64 xx = 0; int cc = 0;
-#pragma unroll
-    for (int w = 0; w < NT / 32; w++) { xx ^= sm.r_x[p][w]; cc += sm.r_i[p][w]; }
-    x = xx; cnt = cc;
+    const u64 xs = k.lane < NW ? sm.r_x[p][k.lane] : 0ull;
+    const int cs = k.lane < NW ? sm.r_i[p][k.lane] : 0;
+    x = ((u64)__reduce_xor_sync(0xffffffffu, (unsigned)(xs >> 32)) << 32) | __reduce_xor_sync(0xffffffffu, (unsigned)xs);
+    cnt = __reduce_add_sync(0xffffffffu, cs);
 }
 template <int N, int NT>
 __device__ __forceinline__ int blk_max_i(BlkSmem<N, NT>& sm, Blk<NT>& k, int v)
 {
-    v = warp_max_i(v);
+    constexpr int NW = NT / 32;
+    v = __reduce_max_sync(0xffffffffu, v);
     const int p = k.ph; k.ph ^= 1;
     if (k.lane == 0) sm.r_i[p][k.warp] = v;
     k.sync();
-    int m = sm.r_i[p][0];
-#pragma unroll
-    for (int w = 1; w < NT / 32; w++) m = max(m, sm.r_i[p][w]);
-    return m;
+    return __reduce_max_sync(0xffffffffu, k.lane < NW ? sm.r_i[p][k.lane] : (int)0x80000000);
 }
 template <int N, int NT>
 __device__ __forceinline__ void blk_sum_max(BlkSmem<N, NT>& sm, Blk<NT>& k, int& s, int& mx)
 {
-    s = warp_sum_i(s); mx = warp_max_i(mx);
+    constexpr int NW = NT / 32;
+    s = __reduce_add_sync(0xffffffffu, s); mx = __reduce_max_sync(0xffffffffu, mx);
     const int p = k.ph; k.ph ^= 1;
     if (k.lane == 0) { sm.r_i[p][k.warp] = s; sm.r_j[p][k.warp] = mx; }
     k.sync();
-    int ss = 0, mm = sm.r_j[p][0];
-#pragma unroll
-    for (int w = 0; w < NT / 32; w++) { ss += sm.r_i[p][w]; mm = max(mm, sm.r_j[p][w]); }
-    s = ss; mx = mm;
+    s = __reduce_add_sync(0xffffffffu, k.lane < NW ? sm.r_i[p][k.lane] : 0);
+    mx = __reduce_max_sync(0xffffffffu, k.lane < NW ? sm.r_j[p][k.lane] : (int)0x80000000);
 }
 // argmax with numpy semantics (first index wins ties); idx = INT_MAX marks an empty thread.  Warp stage: three REDUX
-// instructions on order-preserving integer keys (tg_common.cuh warp_argmax_key); block stage: one slot per warp.
+// instructions on order-preserving integer keys (tg_common.cuh warp_argmax_key); block stage: the same on the NW slots.
 template <int N, int NT>
 __device__ __forceinline__ int blk_argmax_d(BlkSmem<N, NT>& sm, Blk<NT>& k, double v, int idx)
 {
+    constexpr int NW = NT / 32;
     u64 key = idx != 0x7fffffff ? order_key(v) : 0ull;
     warp_argmax_key(key, idx);
     const int p = k.ph; k.ph ^= 1;
     if (k.lane == 0) { sm.r_x[p][k.warp] = key; sm.r_i[p][k.warp] = idx; }
     k.sync();
-    u64 bk = sm.r_x[p][0]; int bi = sm.r_i[p][0];
-#pragma unroll
-    for (int w = 1; w < NT / 32; w++) {
-        const u64 ok = sm.r_x[p][w]; const int oi = sm.r_i[p][w];
-        if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
-    }
-    return bi;
+    u64 k2 = k.lane < NW ? sm.r_x[p][k.lane] : 0ull;
+    int i2 = k.lane < NW ? sm.r_i[p][k.lane] : 0x7fffffff;
+    warp_argmax_key(k2, i2);
+    return i2;
 }
 template <int N, int NT>
 __device__ __forceinline__ int blk_min_i(BlkSmem<N, NT>& sm, Blk<NT>& k, int v)
 {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    constexpr int NW = NT / 32;
+    v = __reduce_min_sync(0xffffffffu, v);
     const int p = k.ph; k.ph ^= 1;
     if (k.lane == 0) sm.r_i[p][k.warp] = v;
     k.sync();
-    int m = sm.r_i[p][0];
-#pragma unroll
-    for (int w = 1; w < NT / 32; w++) m = min(m, sm.r_i[p][w]);
-    return m;
+    return __reduce_min_sync(0xffffffffu, k.lane < NW ? sm.r_i[p][k.lane] : 0x7fffffff);
 }
 
 // ---- board ------------------------------------------------------------------------------------------------------
@@ -212,35 +208,40 @@ __device__ inline void bb_put_stone(BlkSmem<N, NT>& sm, WBoard<N>& b, BScal& s, 
     k.sync();                                                // every thread has read the neighbourhood
     int prisoner = 0;
     if (ncap == 0 && nown <= 1) {
-        if (k.tid == 0) {
-            b.color[pos] = (uint8_t)color; b.chain[pos] = (uint16_t)label;
-            int el[4], ne = 0;                               // local liberty update, see wb_put_stone
-            unsigned gained = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int cc = b.color[q[i]];
+        // local liberty update (see wb_put_stone), one lane of warp 0 per neighbour: every distinct adjacent enemy string
+        // loses the liberty pos; the stone's string loses pos, gains the empty neighbours that were not its liberties yet
+        // and grows by one
+        if (k.warp == 0) {
+            bool gain = false;
+            if (k.lane < 4) {
+                const int qi = q[k.lane];
+                const int cc = b.color[qi];
                 if (cc == other) {
-                    const int l = b.chain[q[i]];
+                    const int l = b.chain[qi];
                     bool dup = false;
-                    for (int j = 0; j < ne; j++) dup |= (el[j] == l);
-                    if (!dup) { el[ne++] = l; b.ls[l] -= 1u << 16; }
+                    for (int j = 0; j < k.lane; j++) dup |= (b.color[q[j]] == other && b.chain[q[j]] == l);
+                    if (!dup) b.ls[l] -= 1u << 16;           // distinct labels per lane: no two lanes touch the same word
                 } else if (cc == EMPTY) {
                     bool already = false;
                     if (nown == 1) {
-                        const int r[4] = { q[i] - G::W, q[i] - 1, q[i] + 1, q[i] + G::W };
+                        const int r[4] = { qi - G::W, qi - 1, qi + 1, qi + G::W };
 #pragma unroll
                         for (int j = 0; j < 4; j++)
                             already |= (r[j] != pos && b.color[r[j]] == color && b.chain[r[j]] == label);
                     }
-                    if (!already) gained++;
+                    gain = !already;
                 }
             }
-            if (nown == 1) b.ls[label] += (gained << 16) - (1u << 16) + 1u;
-            else b.ls[label] = (gained << 16) | 1u;
-            if (s.moves < G::MAXREC) { hist_hash[s.moves] = s.hash; hist_pos[s.moves] = (int16_t)pos; }
-            const unsigned bit = bloom_bit(s.hash);
-            b.bloom[bit >> 5] |= 1u << (bit & 31);
-            __threadfence_block();
+            const unsigned gained = (unsigned)__popc(__ballot_sync(0xffffffffu, gain));
+            if (k.lane == 0) {
+                b.color[pos] = (uint8_t)color; b.chain[pos] = (uint16_t)label;
+                if (nown == 1) b.ls[label] += (gained << 16) - (1u << 16) + 1u;
+                else b.ls[label] = (gained << 16) | 1u;
+                if (s.moves < G::MAXREC) { hist_hash[s.moves] = s.hash; hist_pos[s.moves] = (int16_t)pos; }
+                const unsigned bit = bloom_bit(s.hash);
+                b.bloom[bit >> 5] |= 1u << (bit & 31);
+                __threadfence_block();
+            }
         }
         k.sync();
         s.moves++;
@@ -326,10 +327,6 @@ __device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const typename BlkSmem
         if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }
     }
     if (prof) { const long long c = clock64(); prof[8] += c - c0; c0 = c; }
-#ifdef TG_PROF_FINE
-    k.sync();
-    if (prof) { const long long c = clock64(); prof[11] += c - c0; c0 = c; }
-#endif
     const int r = blk_argmax_d<N, NT>(sm, k, bv, bi);
     if (prof) { const long long c = clock64(); prof[9] += c - c0; }
     return r;
@@ -364,7 +361,7 @@ __device__ inline int expand_node_blk(BlkSmem<N, NT>& sm, const Dev& D, const Tr
                 }
             } else if (superko && (col == BLACK || col == WHITE)) {
                 const int l = b.chain[c];
-                if ((b.ls[l] >> 16) == 1u) atomicXor(&an.cx[l], D.zob[other * G::CELLS + c]);
+                if ((b.ls[l] >> 16) == 1u) atomicXor(&an.cx[l], sm.zob[other * G::CELLS + c]);
             }
         }
     }
@@ -378,7 +375,7 @@ __device__ inline int expand_node_blk(BlkSmem<N, NT>& sm, const Dev& D, const Tr
         const int pi = c * NT + k.tid;
         cand[c] = false;
         if (pi < G::NN) {
-            const PointStatus st = wb_point_status<N>(b, an, s, onboard_pos<N>(pi), color, superko, D.zob, EyeLutPacked{sm.eye2});
+            const PointStatus st = wb_point_status<N>(b, an, s, onboard_pos<N>(pi), color, superko, sm.zob, EyeLutPacked{sm.eye2});
             cand[c] = st.legal_pre && st.satari < 7 && !st.eye;                     // tree.py:261-263 (legality completed below)
             sm.flag[pi] = 0;
             if (cand[c] && st.need_scan) { const int hI = atomicAdd(&sm.nhit, 1); hit_h[hI] = st.h; hit_pt[hI] = (int16_t)pi; }
@@ -403,9 +400,9 @@ __device__ inline int expand_node_blk(BlkSmem<N, NT>& sm, const Dev& D, const Tr
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (k.lane == 0) sm.wcnt[k.warp] = __popc(m);
         k.sync();
-        int before = 0, all = 0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) { const int v = sm.wcnt[w]; all += v; if (w < k.warp) before += v; }
+        const int wv = k.lane < NW ? sm.wcnt[k.lane] : 0;                           // lane-parallel fold of the warp counts
+        const int all = __reduce_add_sync(0xffffffffu, wv);
+        const int before = __reduce_add_sync(0xffffffffu, k.lane < k.warp ? wv : 0);
         if (ok) t.action[row + total + before + __popc(m & ((1u << k.lane) - 1))] = (int16_t)onboard_pos<N>(pi);
         total += all;
         k.sync();
@@ -500,6 +497,7 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, const uint32_t* 
     const Tree t = tree_of<G::AP>(D.tree, g);
     stage_node<N, NT>(sm.st[0], t, 0, k);                    // the root's rows arrive while the board is loaded
     for (int i = k.tid; i < 4096 / 4; i += NT) reinterpret_cast<uint4*>(sm.eye2)[i] = reinterpret_cast<const uint4*>(eye2)[i];
+    for (int i = k.tid; i < 4 * G::CELLS; i += NT) sm.zob[i] = D.zob[i];
     BScal rs;
     bb_load<N, NT>(sm.root, rs, pool_of<N>(D), g, k);
     const int root_color = gs[GS_COLOR];
@@ -548,7 +546,7 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, const uint32_t* 
                 t.hdr[(size_t)cur * H_STRIDE + H_VL] = st.hdr[H_VL] + 1; t.cvl[row + next] = st.vl[next] + 1;    // :221 add_virtual_loss
             }
             plen++;
-            bb_put_stone<N, NT>(sm, sm.scratch, s, mv, color, D.zob, hh, hp, k);      // :217
+            bb_put_stone<N, NT>(sm, sm.scratch, s, mv, color, sm.zob, hh, hp, k);     // :217
             if (prof) { const long long c = clock64(); D.prof[2] += c - pt0; pt0 = c; }
             color = opp(color);
             int expand_threshold = 1;

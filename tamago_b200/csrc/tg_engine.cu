@@ -71,6 +71,7 @@ struct tg_engine {
     int64_t last_eval_slots = 0;
     int sms = 148;
     bool puct_warp = false;
+    int puct_nt = 256;                           // threads per game of the block-per-game PUCT kernels (128, 256 or 512)
     const uint32_t* eye2 = nullptr;              // eye table packed to two bits per code (block-per-game kernels keep it in shared memory)
 };
 
@@ -155,6 +156,7 @@ template <int BN> static int setup_kernel_attrs()
 template <int BN> static int setup_blk_attr()
 {
     static_assert(sizeof(BlkSmem<BN, 512>) <= 96 * 1024, "block-per-game scratch");
+    CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem<BN, 128>)));
     CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem<BN, 256>)));
     CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem<BN, 512>)));
     return 0;
@@ -318,6 +320,8 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     // PUCT kernels: one warp per game when the pool fills the machine with warps (throughput), one CTA per game when it
     // does not (latency): BASELINE configs[3] (1024 games) runs warp-per-game, configs[4] (one game) block-per-game
     e->puct_warp = getenv("TG_PUCT_WARP") != nullptr || (games > 3 * e->sms && getenv("TG_PUCT_BLOCK") == nullptr);
+    e->puct_nt = games <= e->sms ? 512 : 256;
+    if (const char* nt = getenv("TG_PUCT_NT")) e->puct_nt = atoi(nt);
     {
         std::vector<uint8_t> tab; build_eye_table(tab);
         std::vector<uint32_t> packed(4096, 0u);
@@ -650,6 +654,16 @@ template <int BN> static int launch_eval(tg_engine* e, int use_logit, int max_sl
     return 0;
 }
 
+// one PUCT batch with the block-per-game kernels: descents, evaluation, backup
+template <int BN, int NT> static int puct_iter_blk(tg_engine* e, int visits, int batch, int strict, int max_slots, int* ev)
+{
+    const Dev& D = e->D;
+    k_descend_puct_blk<BN, NT><<<D.games, NT, sizeof(BlkSmem<BN, NT>), e->stream>>>(D, e->eye2, visits, batch, strict);
+    const int rc = launch_eval<BN>(e, 0, max_slots, ev);
+    k_backup_blk<BN, NT><<<D.games, NT, 256 * 136, e->stream>>>(D, 0);
+    return rc;
+}
+
 // Queue one move of every game on the engine's stream (no host synchronisation); tg_collect waits for it.
 extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int32_t strict, int32_t play, int32_t root_arrays)
 {
@@ -692,14 +706,12 @@ extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int3
                         k_descend_puct<BN><<<grid, thr, sm, e->stream>>>(D, visits, batch, strict);
                         rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
                         k_backup<BN><<<grid, thr, 0, e->stream>>>(D, 0);
-                    } else if (games <= e->sms) {        // block-per-game, 512 threads per ply (tg_block.cuh): single-game genmove
-                        k_descend_puct_blk<BN, 512><<<games, 512, sizeof(BlkSmem<BN, 512>), e->stream>>>(D, e->eye2, visits, batch, strict);
-                        rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
-                        k_backup_blk<BN, 512><<<games, 512, 256 * 136, e->stream>>>(D, 0);
-                    } else {                             // block-per-game, 256 threads: up to three CTAs per SM
-                        k_descend_puct_blk<BN, 256><<<games, 256, sizeof(BlkSmem<BN, 256>), e->stream>>>(D, e->eye2, visits, batch, strict);
-                        rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
-                        k_backup_blk<BN, 256><<<games, 256, 256 * 136, e->stream>>>(D, 0);
+                    } else {                             // block-per-game (tg_block.cuh): a ply runs puct_nt threads wide
+                        const int ms_ = (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap);
+                        int* evp = iters <= 24 ? &ev : nullptr;
+                        if (e->puct_nt == 512) rc = puct_iter_blk<BN, 512>(e, visits, batch, strict, ms_, evp);
+                        else if (e->puct_nt == 128) rc = puct_iter_blk<BN, 128>(e, visits, batch, strict, ms_, evp);
+                        else rc = puct_iter_blk<BN, 256>(e, visits, batch, strict, ms_, evp);
                     }
                     e->launches += 2;
                 }
@@ -740,8 +752,8 @@ extern "C" int tg_collect(tg_engine* e, tg_step_result* out)
         CK(cudaMemcpy(h, D.prof, sizeof h, cudaMemcpyDeviceToHost));
         CK(cudaMemset(D.prof, 0, 64 * sizeof(long long)));
         fprintf(stderr, "descend profile (game 0, cycles): copy %lld  select %lld (%lld)  put_stone %lld  expand %lld (%lld)  push_leaf %lld (%lld)"
-                        "  [select: scores %lld  argmax %lld  row wait %lld  barrier after scores %lld]\n",
-                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7], h[8], h[9], h[10], h[11]);
+                        "  [block kernels, select: scores %lld  argmax %lld  row wait %lld]\n",
+                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7], h[8], h[9], h[10]);
     }
     { const int orc = check_net_overflow(e); if (orc) return orc; }
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));
