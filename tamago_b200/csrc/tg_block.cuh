@@ -248,6 +248,53 @@ __device__ inline void bb_put_stone(BlkSmem<N, NT>& sm, WBoard<N>& b, BScal& s, 
         return;                                              // no prisoners: the ko rule (:173-177) cannot apply
     }
     if (k.tid == 0) { b.color[pos] = (uint8_t)color; b.chain[pos] = (uint16_t)label; }
+    if (ncap == 0) {
+        // merge without capture: one sweep relabels the absorbed strings and recounts the merged string's liberties
+        // (see wb_put_stone); sizes add up; adjacent enemy strings lose pos
+        unsigned size = 1;
+        for (int j = 0; j < nown; j++) size += b.ls[own[j]] & 0xffffu;
+        u64 none = 0; int cnt = 0;
+        for (int c = k.tid; c < G::CELLS; c += NT) {
+            const int cc = c == pos ? color : b.color[c];    // (thread 0's store of the new stone may not have landed yet)
+            if (cc == color && c != pos) {
+                const int l = b.chain[c];
+                bool hit = false;
+                for (int j = 1; j < nown; j++) hit |= (own[j] == l);
+                if (hit) b.chain[c] = (uint16_t)label;
+            } else if (cc == EMPTY) {
+                const int r[4] = { c - G::W, c - 1, c + 1, c + G::W };
+                bool adj = false;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (r[j] == pos) { adj = true; continue; }
+                    if (b.color[r[j]] != color) continue;
+                    const int l = b.chain[r[j]];
+                    for (int m = 0; m < nown; m++) adj |= (own[m] == l);
+                }
+                cnt += adj;
+            }
+        }
+        blk_xor_sum<N, NT>(sm, k, none, cnt);                // (contains a barrier: all reads of ls[own[]] are done)
+        if (k.tid == 0) {
+            b.ls[label] = ((unsigned)cnt << 16) | size;
+            int el[4], ne = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (b.color[q[i]] != other) continue;
+                const int l = b.chain[q[i]];
+                bool dup = false;
+                for (int j = 0; j < ne; j++) dup |= (el[j] == l);
+                if (!dup) { el[ne++] = l; b.ls[l] -= 1u << 16; }
+            }
+            if (s.moves < G::MAXREC) { hist_hash[s.moves] = s.hash; hist_pos[s.moves] = (int16_t)pos; }
+            const unsigned bit = bloom_bit(s.hash);
+            b.bloom[bit >> 5] |= 1u << (bit & 31);
+            __threadfence_block();
+        }
+        s.moves++;
+        k.sync();
+        return;                                              // no prisoners: the ko rule (:173-177) cannot apply
+    }
     {
         u64 hx = 0; int cnt = 0;
         for (int c = k.tid; c < G::CELLS; c += NT) {

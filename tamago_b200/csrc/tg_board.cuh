@@ -191,6 +191,54 @@ __device__ inline void wb_put_stone(WBoard<N>& b, BScal& s, int pos, int color, 
     if (lane == 0) { b.color[pos] = (uint8_t)color; b.chain[pos] = (uint16_t)label; }
     s.hash ^= zob[color * G::CELLS + pos];                   // :147
     int prisoner = 0;
+    if (ncap == 0 && nown > 1) {
+        // Merge without capture (string.py:443-545): ONE sweep relabels the absorbed strings and recounts the liberties of
+        // the merged string -- the empty points next to any stone of the merging strings or to the new stone -- instead of
+        // the relabel sweep plus the two sweeps of the full recount.  Sizes add up; adjacent enemy strings lose pos.
+        __syncwarp();
+        unsigned size = 1;
+        for (int k = 0; k < nown; k++) size += b.ls[own[k]] & 0xffffu;
+        int cnt = 0;
+        for (int c = lane; c < G::CELLS; c += 32) {
+            const int cc = b.color[c];
+            if (cc == color && c != pos) {
+                const int l = b.chain[c];
+                bool hit = false;
+                for (int k = 1; k < nown; k++) hit |= (own[k] == l);
+                if (hit) b.chain[c] = (uint16_t)label;
+            } else if (cc == EMPTY) {
+                const int r[4] = { c - G::W, c - 1, c + 1, c + G::W };
+                bool adj = false;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (r[j] == pos) { adj = true; continue; }
+                    if (b.color[r[j]] != color) continue;
+                    const int l = b.chain[r[j]];                 // an absorbed label or already `label`: both are in own[]
+                    for (int k = 0; k < nown; k++) adj |= (own[k] == l);
+                }
+                cnt += adj;
+            }
+        }
+        const unsigned libs = (unsigned)warp_sum_i(cnt);
+        if (lane == 0) {
+            b.ls[label] = (libs << 16) | size;
+            int el[4], ne = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (b.color[q[i]] != other) continue;
+                const int l = b.chain[q[i]];
+                bool dup = false;
+                for (int k = 0; k < ne; k++) dup |= (el[k] == l);
+                if (!dup) { el[ne++] = l; b.ls[l] -= 1u << 16; }
+            }
+            if (s.moves < G::MAXREC) { hist_hash[s.moves] = s.hash; hist_pos[s.moves] = (int16_t)pos; }   // record.py:30-44
+            const unsigned bit = bloom_bit(s.hash);
+            b.bloom[bit >> 5] |= 1u << (bit & 31);
+        }
+        s.moves++;
+        __syncwarp();
+        return;                                              // no prisoners: the ko rule (:173-177) cannot apply
+    }
     if (ncap > 0 || nown > 1) {
         __syncwarp();
         u64 hx = 0; int cnt = 0;
@@ -218,28 +266,29 @@ __device__ inline void wb_put_stone(WBoard<N>& b, BScal& s, int pos, int color, 
         // so the full recount sweep is replaced by a local update with the same result.  Every distinct adjacent
         // enemy string loses the liberty pos; the stone's string loses pos, gains the empty neighbours of pos that
         // were not its liberties yet (string.py:411-441 add_stone / 371-409 make_string) and grows by one.
-        if (lane == 0) {
-            int el[4], ne = 0;
-            unsigned gained = 0;
+        // One lane per neighbour (the four checks are independent), combined with a ballot.
+        bool gain = false;
+        if (lane < 4) {
+            const int qi = q[lane];
+            const int cc = b.color[qi];
+            if (cc == other) {
+                const int l = b.chain[qi];
+                bool dup = false;
+                for (int k = 0; k < lane; k++) dup |= (b.color[q[k]] == other && b.chain[q[k]] == l);
+                if (!dup) b.ls[l] -= 1u << 16;               // distinct labels per lane: no two lanes touch the same word
+            } else if (cc == EMPTY) {
+                bool already = false;
+                if (nown == 1) {
+                    const int r[4] = { qi - G::W, qi - 1, qi + 1, qi + G::W };
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int cc = b.color[q[i]];
-                if (cc == other) {
-                    const int l = b.chain[q[i]];
-                    bool dup = false;
-                    for (int k = 0; k < ne; k++) dup |= (el[k] == l);
-                    if (!dup) { el[ne++] = l; b.ls[l] -= 1u << 16; }
-                } else if (cc == EMPTY) {
-                    bool already = false;
-                    if (nown == 1) {
-                        const int r[4] = { q[i] - G::W, q[i] - 1, q[i] + 1, q[i] + G::W };
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            already |= (r[j] != pos && b.color[r[j]] == color && b.chain[r[j]] == label);
-                    }
-                    if (!already) gained++;
+                    for (int j = 0; j < 4; j++)
+                        already |= (r[j] != pos && b.color[r[j]] == color && b.chain[r[j]] == label);
                 }
+                gain = !already;
             }
+        }
+        const unsigned gained = (unsigned)__popc(__ballot_sync(0xffffffffu, gain));
+        if (lane == 0) {
             if (nown == 1) b.ls[label] += (gained << 16) - (1u << 16) + 1u;
             else b.ls[label] = (gained << 16) | 1u;
         }

@@ -140,7 +140,7 @@ template <int BN> static int setup_kernel_attrs()
     const int bytes = (int)(sizeof(WarpSmem<BN>) * SEARCH_WARPS);
     CK(cudaFuncSetAttribute(k_root_begin<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_descend_sh<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 4 * Geo<BN>::CP * 8));
     CK(cudaFuncSetAttribute(k_move_end<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_reset<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_play<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -703,7 +703,7 @@ extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int3
                 const int iters = (visits + batch - 1) / batch + 1;
                 for (int it = 0; it < iters && !rc; it++) {
                     if (e->puct_warp) {                  // warp-per-game kernels (TG_PUCT_WARP=1: A/B measurements)
-                        k_descend_puct<BN><<<grid, thr, sm, e->stream>>>(D, visits, batch, strict);
+                        k_descend_puct<BN><<<grid, thr, sm + 4 * Geo<BN>::CP * 8, e->stream>>>(D, visits, batch, strict);
                         rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
                         k_backup<BN><<<grid, thr, 0, e->stream>>>(D, 0);
                     } else {                             // block-per-game (tg_block.cuh): a ply runs puct_nt threads wide
@@ -752,8 +752,8 @@ extern "C" int tg_collect(tg_engine* e, tg_step_result* out)
         CK(cudaMemcpy(h, D.prof, sizeof h, cudaMemcpyDeviceToHost));
         CK(cudaMemset(D.prof, 0, 64 * sizeof(long long)));
         fprintf(stderr, "descend profile (game 0, cycles): copy %lld  select %lld (%lld)  put_stone %lld  expand %lld (%lld)  push_leaf %lld (%lld)"
-                        "  [block kernels, select: scores %lld  argmax %lld  row wait %lld]\n",
-                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7], h[8], h[9], h[10]);
+                        "  [block kernels, select: scores %lld  argmax %lld  row wait %lld]  [warp put_stone: captures %lld (%lld cycles), passes %lld (%lld)]\n",
+                h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7], h[8], h[9], h[10], h[12], h[13], h[14], h[15]);
     }
     { const int orc = check_net_overflow(e); if (orc) return orc; }
     CK(cudaEventElapsedTime(&e->last_ms, e->events[0], e->events[1]));

@@ -320,6 +320,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
 {
     using G = Geo<N>;
     const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    // the Zobrist keys (one read per put_stone, ~100 plies per descent) sit behind the per-warp scratch, shared by the CTA
+    extern __shared__ __align__(16) unsigned char smem_raw_[];
+    u64* zs = reinterpret_cast<u64*>(smem_raw_ + sizeof(WarpSmem<N>) * SEARCH_WARPS);
+    for (int i = threadIdx.x; i < 4 * G::CELLS; i += SEARCH_WARPS * 32) zs[i] = D.zob[i];
+    __syncthreads();
     if (g >= D.games) return;
     int* gs = D.gs + (size_t)g * GS_STRIDE;
     if (lane == 0) { gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
@@ -385,8 +390,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
                 t.hdr[(size_t)cur * H_STRIDE + H_VL] = vl_node + 1; t.cvl[row + next] = vl_edge + 1;       // :221 add_virtual_loss
             }
             plen++;
-            wb_put_stone<N>(sm.scratch, s, mv, color, D.zob, hh, hp, lane);      // :217
-            if (prof) { const long long c = clock64(); D.prof[2] += c - pt0; pt0 = c; }
+            const int pris_before = s.pris0 + s.pris1;
+            wb_put_stone<N>(sm.scratch, s, mv, color, zs, hh, hp, lane);         // :217
+            if (prof) { const long long c = clock64(); D.prof[2] += c - pt0;
+                        if (s.pris0 + s.pris1 != pris_before) { D.prof[12]++; D.prof[13] += c - pt0; } else if (mv == PASS) { D.prof[14]++; D.prof[15] += c - pt0; }
+                        pt0 = c; }
             color = opp(color);
             int expand_threshold = 1;
             if (s.moves > 2) {                                                   // :224-229
