@@ -268,6 +268,9 @@ __device__ inline void bb_put_stone(BlkSmem<N, NT>& sm, WBoard<N>& b, BScal& s, 
                 for (int j = 0; j < 4; j++) {
                     if (r[j] == pos) { adj = true; continue; }
                     if (b.color[r[j]] != color) continue;
+                    // (another thread may be relabelling this stone right now: compute-sanitizer racecheck reports the pair.
+                    //  Benign by construction: the 16-bit label is read either as the absorbed label or as `label`, and both
+                    //  are members of own[].)
                     const int l = b.chain[r[j]];
                     for (int m = 0; m < nown; m++) adj |= (own[m] == l);
                 }

@@ -213,7 +213,8 @@ __device__ inline void wb_put_stone(WBoard<N>& b, BScal& s, int pos, int color, 
                 for (int j = 0; j < 4; j++) {
                     if (r[j] == pos) { adj = true; continue; }
                     if (b.color[r[j]] != color) continue;
-                    const int l = b.chain[r[j]];                 // an absorbed label or already `label`: both are in own[]
+                    const int l = b.chain[r[j]];                 // an absorbed label or already `label` (another lane may be
+                                                                 // relabelling it right now): both are in own[], same verdict
                     for (int k = 0; k < nown; k++) adj |= (own[k] == l);
                 }
                 cnt += adj;
