@@ -130,6 +130,9 @@ void tg_engine_destroy(tg_engine* e);
 int  tg_set_zobrist(tg_engine* e, const uint64_t* table);
 /* nn/utility.py:139-159 load_network: parameters of DualNet */
 int  tg_load_weights(tg_engine* e, const tg_weights* w);
+/* the same from DEVICE pointers (fp32 arrays on the engine's GPU, e.g. the trainer's parameters): the BatchNorm fold and
+ * the operand packing run on the device, no host round trip; results are bit-identical to tg_load_weights */
+int  tg_load_weights_device(tg_engine* e, const tg_weights* w);
 
 /* GoBoard.clear (go_board.py:111) for the games flagged in mask (NULL = all); game_ids key the noise stream.
  * Asynchronous: the arguments are copied before the call returns, the reset is ordered on the engine's stream. */

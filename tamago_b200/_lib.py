@@ -53,6 +53,7 @@ EXPORTS = {
     "tg_engine_destroy": (None, [C.c_void_p]),
     "tg_set_zobrist": (C.c_int, [C.c_void_p, u64p]),
     "tg_load_weights": (C.c_int, [C.c_void_p, C.POINTER(Weights)]),
+    "tg_load_weights_device": (C.c_int, [C.c_void_p, C.POINTER(Weights)]),
     "tg_reset": (C.c_int, [C.c_void_p, u8p, u64p, u8p]),
     "tg_play": (C.c_int, [C.c_void_p, i16p, u8p, i32p, C.c_int32, C.POINTER(PlyDump)]),
     "tg_set_to_move": (C.c_int, [C.c_void_p, i32p]),

@@ -507,6 +507,113 @@ extern "C" int tg_load_weights(tg_engine* e, const tg_weights* w)
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same fold / split / pack on the device, from parameters that already live there (the trainer's tensors):
+// tg_load_weights_device.  Every operation mirrors tg_load_weights (float64 BatchNorm fold, per-layer power-of-two
+// scale from the largest folded weight, fp16 (hi, lo * 2^11) split, UMMA tile layout), so both loaders produce the
+// same bits (tests/test_gpu_dualnet.py::test_device_weight_loader_matches_host_loader).
+// ---------------------------------------------------------------------------------------------
+struct FoldOut {
+    __half* w_stem; __half* w_conv; float* bias; float* scale; float* w32_stem; float* w32_conv;
+    float* head_w; float* head_b; float* pfc_t; float* pfc_b; float* vfc_w; float* vfc_b;
+};
+
+__global__ void __launch_bounds__(256) k_fold_conv(tg_weights w, FoldOut o, int blocks)
+{
+    const int l = blockIdx.x, tid = threadIdx.x;                 // one CTA per convolution layer
+    const int cin = l == 0 ? 6 : 64, chunks = l == 0 ? 2 : 8;
+    const float* cw = l == 0 ? w.conv_w : w.block_conv_w + (size_t)(l - 1) * 64 * 64 * 9;
+    const float* bn = l == 0 ? w.bn : w.block_bn + (size_t)(l - 1) * 4 * 64;
+    const double eps = (double)(l == 0 ? w.bn_eps : w.block_bn_eps);
+    __shared__ double g[64];
+    __shared__ double red[256];
+    if (tid < 64) {
+        g[tid] = (double)bn[tid] / sqrt((double)bn[3 * 64 + tid] + eps);
+        o.bias[(size_t)l * 64 + tid] = (float)((double)bn[64 + tid] - (double)bn[2 * 64 + tid] * g[tid]);
+    }
+    __syncthreads();
+    double mx = 0.0;
+    for (int i = tid; i < 64 * cin * 9; i += 256) mx = fmax(mx, fabs((double)cw[i] * g[i / (cin * 9)]));
+    red[tid] = mx;
+    __syncthreads();
+    for (int st = 128; st >= 1; st >>= 1) { if (tid < st) red[tid] = fmax(red[tid], red[tid + st]); __syncthreads(); }
+    mx = red[0];
+    int ex = 0;
+    if (mx > 0.0) ex = (int)(((unsigned long long)__double_as_longlong(mx) >> 52) & 0x7ffull) - 1022;    // frexp: mx = f 2^ex, f in [0.5, 1)
+    const double s = __longlong_as_double((long long)((unsigned long long)(14 - ex + 1023) << 52));     // ldexp(1.0, 14 - ex)
+    if (tid == 0) o.scale[l] = (float)s;
+    const size_t stem_tap = (size_t)W_STEM_TAP_BYTES / 2, conv_tap = (size_t)W_TAP_BYTES / 2;
+    __half* lw = l == 0 ? o.w_stem : o.w_conv + (size_t)(l - 1) * W_LAYER_HALVES;
+    float* d32 = l == 0 ? o.w32_stem : o.w32_conv + (size_t)(l - 1) * 64 * 9 * 64;
+    const int per_tap = 64 * chunks * 8;
+    for (int i = tid; i < 9 * per_tap; i += 256) {
+        const int tap = i / per_tap, r = i - tap * per_tap, oc = r / (chunks * 8), ic = r - oc * (chunks * 8);
+        const double v = ic < cin ? (double)cw[((size_t)oc * cin + ic) * 9 + tap] * g[oc] : 0.0;
+        const double vs = v * s;
+        const __half hi = __float2half_rn((float)vs);
+        const __half lo = __float2half_rn((float)((vs - (double)__half2float(hi)) * (double)LO_SCALE));
+        const size_t hl_hi = ((size_t)(ic / 8) * 128 + oc) * 8 + (ic % 8), hl_lo = hl_hi + 64 * 8;
+        const size_t base = (size_t)tap * (l == 0 ? stem_tap : conv_tap);
+        lw[base + hl_hi] = hi; lw[base + hl_lo] = lo;
+        if (ic < cin) d32[((size_t)ic * 9 + tap) * 64 + oc] = (float)v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fold_heads(tg_weights w, FoldOut o, int NN, int A)
+{
+    const int tid = blockIdx.x * 256 + threadIdx.x, nthreads = gridDim.x * 256;
+    if (tid < 3) {
+        const int k = tid;
+        const float* bn = k < 2 ? w.policy_bn : w.value_bn;
+        const int C = k < 2 ? 2 : 1, c = k < 2 ? k : 0;
+        const double g = (double)bn[c] / sqrt((double)bn[3 * C + c] + (double)w.head_bn_eps);
+        const float* cw = k < 2 ? w.policy_conv_w + (size_t)k * 64 : w.value_conv_w;
+        for (int i = 0; i < 64; i++) o.head_w[(size_t)k * 64 + i] = (float)((double)cw[i] * g);
+        o.head_b[k] = (float)((double)bn[C + c] - (double)bn[2 * C + c] * g);
+        o.vfc_b[k] = w.value_fc_b[k];
+    }
+    const int A4 = (A + 3) & ~3;
+    for (int i = tid; i < A * 2 * NN; i += nthreads) { const int oo = i / (2 * NN), j = i - oo * 2 * NN; o.pfc_t[(size_t)j * A4 + oo] = w.policy_fc_w[i]; }
+    for (int i = tid; i < A; i += nthreads) o.pfc_b[i] = w.policy_fc_b[i];
+    for (int i = tid; i < 3 * NN; i += nthreads) o.vfc_w[i] = w.value_fc_w[i];
+}
+
+extern "C" int tg_load_weights_device(tg_engine* e, const tg_weights* w)
+{
+    if (!e || !w) return fail(TG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    free_net(e);
+    const int blocks = e->cfg.net_blocks, L = 1 + 2 * blocks, NN = e->NN, A = e->A, A4 = (A + 3) & ~3;
+    FoldOut o{};
+    auto dz = [&](void** p, size_t bytes) {
+        if (cudaMalloc(p, std::max<size_t>(bytes, 1)) != cudaSuccess) return 1;
+        e->net_allocs.push_back(*p);
+        return cudaMemsetAsync(*p, 0, bytes, e->stream) != cudaSuccess ? 1 : 0;
+    };
+    int bad = 0;
+    bad |= dz((void**)&o.w_stem, 9 * (size_t)W_STEM_TAP_BYTES); bad |= dz((void**)&o.w_conv, (size_t)(L - 1) * W_LAYER_HALVES * 2);
+    bad |= dz((void**)&o.bias, (size_t)L * 64 * 4); bad |= dz((void**)&o.scale, (size_t)L * 4);
+    bad |= dz((void**)&o.w32_stem, (size_t)6 * 9 * 64 * 4); bad |= dz((void**)&o.w32_conv, (size_t)(L - 1) * 64 * 9 * 64 * 4);
+    bad |= dz((void**)&o.head_w, 3 * 64 * 4); bad |= dz((void**)&o.head_b, 3 * 4); bad |= dz((void**)&o.pfc_t, (size_t)2 * NN * A4 * 4);
+    bad |= dz((void**)&o.pfc_b, (size_t)A * 4); bad |= dz((void**)&o.vfc_w, (size_t)3 * NN * 4); bad |= dz((void**)&o.vfc_b, 3 * 4);
+    void* skip = nullptr; void* ovf = nullptr;
+    bad |= dz(&skip, (size_t)e->sms * SKIP_FLOATS_PER_CTA * sizeof(float)); bad |= dz(&ovf, 4);
+    if (bad) { free_net(e); return fail(TG_ERR_CUDA, "weight buffers"); }
+    k_fold_conv<<<L, 256, 0, e->stream>>>(*w, o, blocks);
+    k_fold_heads<<<64, 256, 0, e->stream>>>(*w, o, NN, A);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    NetDev& n = e->net;
+    n.blocks = blocks;
+    n.w_stem = o.w_stem; n.w_conv = o.w_conv; n.bias = o.bias; n.scale = o.scale; n.head_w = o.head_w; n.head_b = o.head_b;
+    n.pfc_t = o.pfc_t; n.pfc_b = o.pfc_b; n.vfc_w = o.vfc_w; n.vfc_b = o.vfc_b; n.w32_stem = o.w32_stem; n.w32_conv = o.w32_conv;
+    n.skip = reinterpret_cast<float*>(skip); n.dbg = nullptr; n.overflow = reinterpret_cast<int*>(ovf);
+    CK(cudaStreamSynchronize(e->stream));
+    e->have_weights = true;
+    return TG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 extern "C" int tg_reset(tg_engine* e, const uint8_t* mask, const uint64_t* game_ids, const uint8_t* never_resign)
 {
     if (!e) return fail(TG_ERR_ARG, "null engine");

@@ -76,6 +76,34 @@ class Engine:
         w.bn_eps, w.block_bn_eps, w.head_bn_eps = 1e-5, 2e-5, 2e-5     # dual_net.py:32, res_block.py:23-24, head/*.py
         check(self.lib.tg_load_weights(self.h, C.byref(w)))
 
+    def load_state_dict_device(self, sd):
+        """The same from torch CUDA tensors on this engine's device (e.g. TrainDualNet.state_dict() right after a training
+        step): the fold and packing run on the device (tg_load_weights_device), nothing crosses PCIe."""
+        import torch
+        dev = torch.device("cuda", self.device)
+
+        def get(name):
+            return sd[name].detach().to(device=dev, dtype=torch.float32).contiguous()
+
+        def bn(prefix):
+            return torch.stack([get(prefix + ".weight"), get(prefix + ".bias"), get(prefix + ".running_mean"), get(prefix + ".running_var")]).contiguous()
+        B = self.net_blocks
+        keep = dict(
+            conv_w=get("conv_layer.weight"), bn=bn("bn_layer"),
+            block_conv_w=torch.stack([torch.stack([get(f"blocks.{b}.conv1.weight"), get(f"blocks.{b}.conv2.weight")]) for b in range(B)]).contiguous(),
+            block_bn=torch.stack([torch.stack([bn(f"blocks.{b}.bn1"), bn(f"blocks.{b}.bn2")]) for b in range(B)]).contiguous(),
+            policy_conv_w=get("policy_head.conv_layer.weight").reshape(2, 64).contiguous(), policy_bn=bn("policy_head.bn_layer"),
+            policy_fc_w=get("policy_head.fc_layer.weight"), policy_fc_b=get("policy_head.fc_layer.bias"),
+            value_conv_w=get("value_head.conv_layer.weight").reshape(1, 64).contiguous(), value_bn=bn("value_head.bn_layer"),
+            value_fc_w=get("value_head.fc_layer.weight"), value_fc_b=get("value_head.fc_layer.bias"))
+        assert tuple(keep["policy_fc_w"].shape) == (self.A, 2 * self.nn) and tuple(keep["block_conv_w"].shape) == (B, 2, 64, 64, 3, 3)
+        w = _lib.Weights()
+        for k, v in keep.items():
+            setattr(w, k, C.cast(C.c_void_p(v.data_ptr()), C.POINTER(C.c_float)))
+        w.bn_eps, w.block_bn_eps, w.head_bn_eps = 1e-5, 2e-5, 2e-5
+        torch.cuda.synchronize(dev)                      # the stacks above were queued on torch's stream
+        check(self.lib.tg_load_weights_device(self.h, C.byref(w)))
+
     # -- boards -----------------------------------------------------------------------------------
     def reset(self, mask=None, game_ids=None, never_resign=None):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)

@@ -27,7 +27,10 @@ def _dist():
 
 
 def run_iteration(program_dir, size=9, visits=16, num_data=10000, batch_size=256, pool_size=4096, data="direct", window_size=300000,
-                  dedup=True, scoring=0, seed=None, amp=True, max_train_steps=None, device_index=None):
+                  dedup=True, scoring=0, seed=None, amp=True, max_train_steps=None, device_index=None, net_on_device=None):
+    """net_on_device: the TrainDualNet the previous iteration returned (out["net"]).  Its parameters are handed to the
+    self-play engine on the device (tg_load_weights_device: fold + packing on the GPU, no host round trip); without it the
+    engine reads model/rl-model.bin like the reference's workers do."""
     import torch
     import torch.distributed as dist
     from .selfplay.shard import shard_for_rank, gather_sample_tensors
@@ -53,12 +56,17 @@ def run_iteration(program_dir, size=9, visits=16, num_data=10000, batch_size=256
     out = {"iteration_dir": save_dir, "world": world}
     # 1. self-play
     t0 = time.perf_counter()
-    net = load_network(os.path.join(program_dir, "model", "rl-model.bin"), True, board_size=size, device_index=dev)
     mine = shard_for_rank(num_data, rank, world)
     if seed is None:
         seed = int.from_bytes(os.urandom(8), "little")
-    pool = SelfPlayPool(save_dir, size, visits, max(1, min(pool_size, len(mine))), mine, state_dict=net.state_dict_np, device_index=dev,
+    sd_host = None
+    if net_on_device is None:
+        sd_host = load_network(os.path.join(program_dir, "model", "rl-model.bin"), True, board_size=size, device_index=dev).state_dict_np
+    pool = SelfPlayPool(save_dir, size, visits, max(1, min(pool_size, len(mine))), mine, state_dict=sd_host, device_index=dev,
                         dedup=dedup, seed=seed + rank, scoring=scoring, sample_cap=8 * len(mine) if data == "direct" else 0)
+    if net_on_device is not None:
+        pool.eng.load_state_dict_device(net_on_device.state_dict())
+    out["weights_from"] = "device" if net_on_device is not None else "model.bin"
     pool.start()
     while pool.active.any():
         pool.step()
@@ -118,8 +126,10 @@ def main():
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
+    net = None
     for it in range(a.iterations):
-        r = run_iteration(a.program_dir, a.size, a.visits, a.num_data, pool_size=a.pool_size, data=a.data, scoring=a.scoring)
+        r = run_iteration(a.program_dir, a.size, a.visits, a.num_data, pool_size=a.pool_size, data=a.data, scoring=a.scoring, net_on_device=net)
+        net = r["net"]
         if _dist()[0] == 0:
             print(json.dumps({k: v for k, v in r.items() if k != "net"}))
     if dist.is_initialized():

@@ -227,3 +227,23 @@ def test_unscaled_seeded_weights_error_scales_with_logit_magnitude(golden_dir, s
         dl = np.abs(logits - ref_logits).max()
         print(f"size {size} evaluator {ev}: max|logit| {np.abs(ref_logits).max():.1f}, max |dlogit| {dl:.3e} (bound {bound:.3e})")
         assert dl <= bound and np.abs(val - ref_val).max() <= 1e-4
+
+
+@pytest.mark.parametrize("size", [9, 19])
+def test_device_weight_loader_matches_host_loader(golden_dir, size):
+    """tg_load_weights_device (BatchNorm fold, power-of-two layer scale, fp16 hi/lo split and UMMA tile packing done by two
+    kernels from torch CUDA tensors) produces the same operand bits as the host loader: outputs of both evaluators are
+    BIT-identical for the same state_dict."""
+    import torch
+    import tamago_b200 as tb
+    g = np.load(os.path.join(golden_dir, f"dualnet_{size}.npz"))
+    sd = _weights(size, 777)
+    x = g["planes"][:24]
+    for ev in (tb.EVAL_DUALNET_TC, tb.EVAL_DUALNET_FP32):
+        e = tb.Engine(board_size=size, games=8, max_visits=8, evaluator=ev)
+        e.load_state_dict(sd)
+        want = e.forward(x, use_logit=True)
+        e.load_state_dict_device({k: torch.from_numpy(np.asarray(v)).cuda() for k, v in sd.items() if not k.endswith("num_batches_tracked")})
+        got = e.forward(x, use_logit=True)
+        e.close()
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), ev

@@ -29,8 +29,11 @@ def test_pipeline_iteration_single_gpu(tmp_path):
     import numpy as np
     import torch
     from tamago_b200.pipeline import run_iteration
+    net = None
     for it in range(2):
-        r = run_iteration(str(tmp_path), size=9, visits=16, num_data=96, batch_size=64, pool_size=48, seed=5 + it, amp=bool(it))
+        r = run_iteration(str(tmp_path), size=9, visits=16, num_data=96, batch_size=64, pool_size=48, seed=5 + it, amp=bool(it), net_on_device=net)
+        net = r["net"]                                          # iteration 2 takes the weights on the device, no file read
+        assert r["weights_from"] == ("device" if it else "model.bin")
         assert r["samples"] == 96 * 8 and r["num_trained_batches"] == 12 * (it + 1) and r["allreduce_bytes_per_step"] == 0
         assert len(os.listdir(r["iteration_dir"])) == 96
     z = np.load(tmp_path / "data" / "rl_data_0.npz")
