@@ -240,7 +240,8 @@ constexpr int BND_WARP = 7;               // rows 224..255: the tail of tile 1, 
 template <int N, int G>
 __global__ void __launch_bounds__(TC_THREADS, 1)       // 21 warps -> 6 on one scheduler -> 80 registers per thread
 k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__ n_slots_ptr, int n_direct, int use_logit,
-             float* __restrict__ policy, float* __restrict__ value)
+             float* __restrict__ policy, float* __restrict__ value,
+             const uint8_t* __restrict__ snap, const int* __restrict__ slot_src, int snap_bytes)
 {
     using NG = NetGeo<N, G>;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -431,10 +432,26 @@ k_dualnet_tc(NetDev P, const float* __restrict__ planes, const int* __restrict__
             const int s0 = grp_ * G;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (interior && s0 + b < n_slots) {
-                const float* pl = planes + (size_t)(s0 + b) * 6 * NG::NN + y * N + x;
-                __half2 h01 = __floats2half2_rn(pl[0], pl[NG::NN]);
-                __half2 h23 = __floats2half2_rn(pl[2 * NG::NN], pl[3 * NG::NN]);
-                __half2 h45 = __floats2half2_rn(pl[4 * NG::NN], pl[5 * NG::NN]);
+                float p0, p1, p2, p3, p4, p5;
+                if (snap) {
+                    // fused feature planes (nn/feature.py:10-57, the arithmetic of k_planes): the search kernels leave one
+                    // leaf snapshot per slot (stone colours + previous move + colour to move, 16 + N^2 bytes); reading it
+                    // here instead of fp32 planes removes the k_planes launch and 95 % of the evaluator's input bytes
+                    const uint8_t* sn = snap + (size_t)slot_src[s0 + b] * snap_bytes;
+                    const int idx = y * N + x, color = sn[3];
+                    int d = sn[16 + idx];
+                    if (color == 2 && d != 0) d = 3 - d;                         // :24-25 colours swap for white to move
+                    p0 = d == 0 ? 1.0f : 0.0f; p1 = d == 1 ? 1.0f : 0.0f; p2 = d == 2 ? 1.0f : 0.0f;     // :31
+                    p3 = (*reinterpret_cast<const int16_t*>(sn) == idx) ? 1.0f : 0.0f;                     // :43-46
+                    p4 = sn[2] ? 1.0f : 0.0f;                                    // :39-41
+                    p5 = color == 2 ? -1.0f : 1.0f;                              // :50-52
+                } else {
+                    const float* pl = planes + (size_t)(s0 + b) * 6 * NG::NN + y * N + x;
+                    p0 = pl[0]; p1 = pl[NG::NN]; p2 = pl[2 * NG::NN]; p3 = pl[3 * NG::NN]; p4 = pl[4 * NG::NN]; p5 = pl[5 * NG::NN];
+                }
+                __half2 h01 = __floats2half2_rn(p0, p1);
+                __half2 h23 = __floats2half2_rn(p2, p3);
+                __half2 h45 = __floats2half2_rn(p4, p5);
                 v.x = *reinterpret_cast<uint32_t*>(&h01); v.y = *reinterpret_cast<uint32_t*>(&h23);
                 v.z = *reinterpret_cast<uint32_t*>(&h45);
             }

@@ -70,7 +70,7 @@ struct tg_engine {
     float last_ms = 0.f, last_eval_ms = 0.f;
     int64_t last_eval_slots = 0;
     int sms = 148;
-    bool puct_warp = false;
+    bool puct_warp = false, unfused_planes = false;   // TG_UNFUSED_PLANES=1: k_planes + fp32 planes for the tensor-core evaluator too (A/B)
     int puct_nt = 256;                           // threads per game of the block-per-game PUCT kernels (128, 256 or 512)
     const uint32_t* eye2 = nullptr;              // eye table packed to two bits per code (block-per-game kernels keep it in shared memory)
 };
@@ -266,7 +266,7 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     DA(D.leaf_node, (size_t)games * e->cap_max); DA(D.leaf_slot, (size_t)games * e->cap_max);
     DA(D.snap, (size_t)games * e->cap_max * e->SNAP);
     DA(D.planes, (size_t)e->slot_cap * e->PLANES); DA(D.policy, (size_t)e->slot_cap * e->A); DA(D.value, (size_t)e->slot_cap * 3);
-    DA(D.n_slots, 1);
+    DA(D.n_slots, 1); DA(D.slot_src, (size_t)e->slot_cap);
     DA(D.out_action, (size_t)games * e->AP); DA(D.out_improved, (size_t)games * e->AP); DA(D.out_visits, (size_t)games * e->AP);
     if (cfg->record_ring) {                       // per-game record of the running game (SelfPlayRecord), rows = move limit
         const size_t rows = (size_t)games * 2 * e->NN;
@@ -320,6 +320,7 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     // PUCT kernels: one warp per game when the pool fills the machine with warps (throughput), one CTA per game when it
     // does not (latency): BASELINE configs[3] (1024 games) runs warp-per-game, configs[4] (one game) block-per-game
     e->puct_warp = getenv("TG_PUCT_WARP") != nullptr || (games > 3 * e->sms && getenv("TG_PUCT_BLOCK") == nullptr);
+    e->unfused_planes = getenv("TG_UNFUSED_PLANES") != nullptr;
     e->puct_nt = games <= e->sms ? 512 : 256;
     if (const char* nt = getenv("TG_PUCT_NT")) e->puct_nt = atoi(nt);
     {
@@ -700,7 +701,7 @@ extern "C" int tg_play(tg_engine* e, const int16_t* moves, const uint8_t* colors
 // ---------------------------------------------------------------------------------------------
 // n_direct < 0: the slot count is read from device memory (written by k_scan); otherwise it is a launch argument, so that
 // back-to-back tg_forward_device calls cannot race on a staged count.
-template <int BN> static int launch_net(tg_engine* e, int use_logit, int max_slots, int n_direct = -1)
+template <int BN> static int launch_net(tg_engine* e, int use_logit, int max_slots, int n_direct = -1, bool from_snapshots = false)
 {
     const Dev& D = e->D;
     const int* n_ptr = n_direct < 0 ? D.n_slots : nullptr;
@@ -713,7 +714,8 @@ template <int BN> static int launch_net(tg_engine* e, int use_logit, int max_slo
         constexpr int G = TcGroup<BN>::G;
         const int groups = (max_slots + G - 1) / G;
         const int grid = std::max(1, std::min(e->sms, groups));
-        k_dualnet_tc<BN, G><<<grid, TC_THREADS, NetGeo<BN, G>::SMEM_BYTES, e->stream>>>(e->net, D.planes, n_ptr, n_direct, use_logit, D.policy, D.value);
+        k_dualnet_tc<BN, G><<<grid, TC_THREADS, NetGeo<BN, G>::SMEM_BYTES, e->stream>>>(e->net, D.planes, n_ptr, n_direct, use_logit, D.policy, D.value,
+            from_snapshots ? D.snap : nullptr, D.slot_src, (int)Snap<BN>::BYTES);
         e->launches++;
     } else {
         if (!e->have_weights) return fail(TG_ERR_STATE, "tg_load_weights has not been called");
@@ -751,11 +753,14 @@ template <int BN> static int launch_eval(tg_engine* e, int use_logit, int max_sl
 {
     const Dev& D = e->D;
     k_scan<<<1, 1024, 0, e->stream>>>(D);
-    k_planes<BN><<<D.games, 256, 16 * Snap<BN>::BYTES, e->stream>>>(D);
+    // the tensor-core evaluator reads the leaf snapshots itself (fused feature planes); the others take fp32 planes
+    const bool fused = e->cfg.evaluator == TG_EVAL_DUALNET_TC && !e->unfused_planes;
+    if (fused) k_slotmap<<<D.games, 256, 0, e->stream>>>(D);
+    else k_planes<BN><<<D.games, 256, 16 * Snap<BN>::BYTES, e->stream>>>(D);
     e->launches += 2;
     const bool timed = ev_idx && *ev_idx + 2 <= (int)e->events.size();
     if (timed) CK(cudaEventRecord(e->events[(*ev_idx)++], e->stream));
-    const int rc = launch_net<BN>(e, use_logit, std::min(max_slots, e->slot_cap));
+    const int rc = launch_net<BN>(e, use_logit, std::min(max_slots, e->slot_cap), -1, fused);
     if (rc) return rc;
     if (timed) CK(cudaEventRecord(e->events[(*ev_idx)++], e->stream));
     return 0;

@@ -48,6 +48,7 @@ struct Dev {
     uint8_t* snap;           // [games][cap][Snap::BYTES]  one per unique slot
     // evaluator batch
     float* planes; float* policy; float* value; int* n_slots;
+    int* slot_src;           // [slot_cap] snapshot index (game * cap + unique leaf) of every evaluator slot (fused plane load)
     int slot_cap;
     // per-move outputs (read back by the host)
     int16_t* out_action;     // [games][AP]
@@ -460,6 +461,17 @@ __global__ void __launch_bounds__(1024) k_scan(Dev D)
         __syncthreads();
     }
     if (threadIdx.x == 0) *D.n_slots = min(carry, D.slot_cap);
+}
+
+// Slot -> snapshot map for the tensor-core evaluator, which builds the feature planes itself from the leaf snapshots
+// (tg_dualnet.cuh, fused plane load): 4 bytes per slot instead of the 6 N^2 fp32 planes k_planes writes.
+__global__ void __launch_bounds__(256) k_slotmap(Dev D)
+{
+    const int g = blockIdx.x;
+    const int* gs = D.gs + (size_t)g * GS_STRIDE;
+    const int nu = gs[GS_NUNIQ], slot0 = gs[GS_SLOT0];
+    for (int u = threadIdx.x; u < nu; u += 256)
+        if (slot0 + u < D.slot_cap) D.slot_src[slot0 + u] = g * D.cap + u;
 }
 
 // K3 feature planes (nn/feature.py:10-57): one block per game expands its leaf snapshots into fp32 planes

@@ -96,3 +96,30 @@ def test_c3_9x9_sh50_many_games():
     prof = np.sort(r["visits"][5][r["visits"][5] > 0])[::-1]
     assert list(prof[:2]) == [7, 7]                                              # {16:1, 8:1, 4:3, 2:7}
     e.close()
+
+
+@pytest.mark.parametrize("size,mode,visits,batch", [(9, 0, 50, 1), (19, 1, 48, 8), (13, 0, 16, 1)])
+def test_fused_feature_planes_equal_the_plane_kernel(monkeypatch, size, mode, visits, batch):
+    """The tensor-core evaluator builds its input planes from the leaf snapshots (fused plane load, tg_dualnet.cuh); with
+    TG_UNFUSED_PLANES=1 it reads the fp32 planes k_planes writes (the kernel pinned to nn/feature.py by the goldens).
+    Same planes => bit-identical searches: moves, root visits, improved policies, after several moves into the game
+    (white to move, previous-move and pass planes in use)."""
+    import tamago_b200 as tb
+    outs = []
+    for unfused in (True, False):
+        if unfused:
+            monkeypatch.setenv("TG_UNFUSED_PLANES", "1")
+        else:
+            monkeypatch.delenv("TG_UNFUSED_PLANES", raising=False)
+        e = tb.Engine(board_size=size, games=24, max_visits=visits, batch_size=batch, evaluator=tb.EVAL_DUALNET_TC, dedup=False, seed=9)
+        e.load_state_dict(_net(size, 3))
+        e.reset(never_resign=np.ones(24, np.uint8))
+        hist = []
+        for step in range(7):
+            r = e.genmove(mode=mode, visits=visits, play=True)
+            assert (r["error"] == 0).all()
+            hist.append((r["move"].copy(), r["visits"].copy(), r["improved"].copy()))
+        outs.append(hist)
+        e.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
