@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_EVAL = {9: 72281646, 13: 150798686, 19: 322548446}      # SURVEY.md B.4 (2 x MAC); 13x13 by the same count
 METRIC = "self-play moves/sec @400 visits (9x9 & 19x19), 1/2/4/8 B200 vs CPU ref"
-DRAM_BYTES_PER_EVAL = {9: 2328.0}        # k_dualnet_tc, ncu --set full capture (profiles/r02_dualnet_tc.md): 953.46 MB / 409 600 evaluations
+DRAM_BYTES_PER_EVAL = {9: 480.2}         # k_dualnet_tc, ncu --set full capture (profiles/r02_dualnet_tc.md): 196.69 MB / 409 600 evaluations
 
 
 def measured_peaks():
@@ -404,7 +404,7 @@ def run_ours(a, out=sys.stdout):
                      "traffic": DRAM_BYTES_PER_EVAL.get(n, 0.0) * (main["evals_per_step"] - games) / 4 if n in DRAM_BYTES_PER_EVAL else None,
                      "traffic_note": "ESTIMATE for one phase launch of this run (a step = 1 root launch of `games` evaluations + 4 phase launches): "
                                      "dram__bytes_read+write per evaluation of the ncu --set full capture in profiles/r02_dualnet_tc.md "
-                                     "(953.5 MB for the 409 600-evaluation launch of phase 3 = 2328 B/eval; algorithmic 2284 B/eval) x evaluations of the launch; "
+                                     "(196.7 MB for the 409 600-evaluation launch of phase 3 = 480 B/eval; algorithmic 441 B/eval: 97 B leaf snapshot + 4 B slot map in, 340 B policy/value out) x evaluations of the launch; "
                                      "not measured inside this run",
                      "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                      "evals_per_step": main["evals_per_step"], "flop_per_eval": flop, "kernel_ms_per_step": main["kernel_ms_per_step"],
