@@ -382,14 +382,23 @@ __device__ inline int select_puct_blk(BlkSmem<N, NT>& sm, const typename BlkSmem
     return r;
 }
 
+// Position-hash history seen by an expansion: entries below `split` are the game's own record (global), the rest the
+// moves of the descent.  The inline descent keeps both in the game's record (split = 0); the deferred expansion of
+// k_expand_leaves_blk keeps the descent's part private, because several CTAs replay leaves of the same game at once.
+struct HistView {
+    const u64* lo; const u64* hi; int split;
+    __device__ __forceinline__ u64 operator[](int e) const { return e < split ? lo[e] : hi[e - split]; }
+};
+
 // ---- expansion (tree.py:247-270 + node.py:41-72) ------------------------------------------------------------------
+// given_idx < 0: allocate the next node of the pool; otherwise fill the rows of a node the tree walk already allocated.
 template <int N, int NT>
 __device__ inline int expand_node_blk(BlkSmem<N, NT>& sm, const Dev& D, const Tree& t, int g, int* gs, const WBoard<N>& b, const BScal& s,
-                                      int color, const u64* hist_hash, unsigned move_key, Blk<NT>& k)
+                                      int color, const HistView hist_hash, unsigned move_key, Blk<NT>& k, int given_idx = -1)
 {
     using G = Geo<N>;
     constexpr int CH = BlkSmem<N, NT>::CH, NW = NT / 32;
-    const int idx = gs[GS_NNODES];
+    const int idx = given_idx >= 0 ? given_idx : gs[GS_NNODES];
     if (idx >= D.tree.max_nodes) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_NODES; k.sync(); return -1; }
     const size_t row = (size_t)idx * G::AP;
     const bool superko = D.superko != 0;
@@ -477,7 +486,7 @@ __device__ inline int expand_node_blk(BlkSmem<N, NT>& sm, const Dev& D, const Tr
         t.cidx[row + i] = NOT_EXPANDED; t.cval[row + i] = 0.0f; t.cvis[row + i] = 0; t.cvl[row + i] = 0; t.cvsum[row + i] = 0.0f;
     }
     if (k.tid < H_STRIDE) t.hdr[(size_t)idx * H_STRIDE + k.tid] = (k.tid == H_K) ? nk : 0;
-    if (k.tid == 0) gs[GS_NNODES] = idx + 1;
+    if (k.tid == 0 && given_idx < 0) gs[GS_NNODES] = idx + 1;
     __threadfence_block();
     k.sync();
     return idx;
@@ -613,7 +622,7 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, const uint32_t* 
                 if (!root_edge) stage_node<N, NT>(sm.st[0], t, 0, k);
                 if (ci == NOT_EXPANDED) {
                     if (prof) pt0 = clock64();
-                    ci = expand_node_blk<N, NT>(sm, D, t, g, gs, sm.scratch, s, color, hh, move_key, k);
+                    ci = expand_node_blk<N, NT>(sm, D, t, g, gs, sm.scratch, s, color, HistView{hh, hh, 0}, move_key, k);
                     if (prof) { const long long c = clock64(); D.prof[3] += c - pt0; pt0 = c; D.prof[6]++; }
                     if (ci < 0) { fail = true; break; }
                     if (k.tid == 0) { t.cidx[row + next] = ci; __threadfence_block(); }
@@ -639,6 +648,275 @@ __global__ void __launch_bounds__(NT) k_descend_puct_blk(Dev D, const uint32_t* 
         k.sync();
     }
     stage_wait();
+}
+
+// =====================================================================================================================
+// Deferred expansion (PUCT batches of more than one descent).
+//
+// Within a batch only the SELECTIONS are sequentially dependent (each one changes the virtual losses the next one reads).
+// What a descent does with the board -- replaying its moves, the legality analysis of the new node, the leaf snapshot for
+// the evaluator -- depends on the path alone, and nothing later in the batch reads the new node's rows unless a later
+// descent walks INTO that node.  So the batch is split in two kernels:
+//   k_walk_puct_blk      one CTA per game: selections only.  A leaf edge allocates the node index, links it into the
+//                        parent row and queues (path, node, flags); no board is touched.  The rows of the nodes a launch
+//                        visits stay in a small shared-memory cache kept coherent by write-through (everything a walk
+//                        changes -- virtual losses, child links -- is written by this CTA), so hot nodes are fetched from
+//                        L2 once per launch instead of once per visit.  If a descent does enter a node allocated earlier
+//                        in the same launch, that node is materialised on the spot (replay + expansion, as the inline
+//                        kernel does for every leaf).
+//   k_expand_leaves_blk  one CTA per queued leaf, all leaves of all games at once: replay the path from the root board,
+//                        fill the node's rows, write the evaluator snapshot.  With one game and 256-leaf batches this is
+//                        where 147 otherwise idle SMs do the board work of the batch in the time of one leaf.
+// Results are bit-identical to the inline kernel (same node numbering, same rows, same queue order).
+// =====================================================================================================================
+constexpr int WALK_MAX_BATCH = 1024;
+enum : int { LEAF_EXPAND = 1, LEAF_SNAP = 2 };
+
+template <int N, int NT> struct WalkSmem {
+    BlkSmem<N, NT> b;
+    int tag[16];                                           // node held by every cache slot (-1: none); slot 0 = root
+    int16_t mv[Geo<N>::MAXREC + 2];                        // moves of the current descent
+    int16_t newleaf[WALK_MAX_BATCH];                       // queue index of the n-th node allocated by this launch
+    int16_t lslot[WALK_MAX_BATCH];                         // unique slot of every queued leaf
+    uint8_t lflag[WALK_MAX_BATCH];                         // LEAF_* flags of every queued leaf
+    unsigned mat[WALK_MAX_BATCH / 32];                     // nodes of this launch already materialised on demand
+    // followed by (nc - 2) more NodeStage slots in dynamic shared memory
+};
+
+template <int N, int NT>
+__device__ __forceinline__ void write_snap_blk(uint8_t* dst, const WBoard<N>& b, int prev, int moves, int color, const Blk<NT>& k)
+{
+    using G = Geo<N>;
+    if (k.tid == 0) {
+        const int pidx = (prev == PASS) ? -1 : ((prev % G::W) - 1) + ((prev / G::W) - 1) * N;
+        *reinterpret_cast<int16_t*>(dst) = (int16_t)pidx;
+        dst[2] = (moves > 1 && prev == PASS) ? 1 : 0;
+        dst[3] = (uint8_t)color;
+    }
+    for (int idx = k.tid; idx < G::NN; idx += NT) dst[Snap<N>::HDR + idx] = b.color[onboard_pos<N>(idx)];
+}
+
+template <int N, int NT>
+__global__ void __launch_bounds__(NT) k_walk_puct_blk(Dev D, const uint32_t* __restrict__ eye2, int visits, int batch, int strict, int nc)
+{
+    using G = Geo<N>;
+    using Stage = typename BlkSmem<N, NT>::NodeStage;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WalkSmem<N, NT>& ws = *reinterpret_cast<WalkSmem<N, NT>*>(smem_raw);
+    BlkSmem<N, NT>& sm = ws.b;
+    Stage* extra = reinterpret_cast<Stage*>(smem_raw + ((sizeof(WalkSmem<N, NT>) + 15) & ~(size_t)15));
+    auto slot_ptr = [&](int sl) -> Stage& { return sl < 2 ? sm.st[sl] : extra[sl - 2]; };
+    Blk<NT> k;
+    const int g = blockIdx.x;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    const bool idle = !gs[GS_ACTIVE] || gs[GS_FINISHED] || gs[GS_ERROR] || gs[GS_DONE];
+    k.sync();
+    if (k.tid == 0) { gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+    __threadfence_block();
+    k.sync();
+    if (idle) return;
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    stage_node<N, NT>(sm.st[0], t, 0, k);                    // the root's rows arrive while the board is loaded
+    for (int i = k.tid; i < 4096 / 4; i += NT) reinterpret_cast<uint4*>(sm.eye2)[i] = reinterpret_cast<const uint4*>(eye2)[i];
+    for (int i = k.tid; i < 4 * G::CELLS; i += NT) sm.zob[i] = D.zob[i];
+    if (k.tid < 16) ws.tag[k.tid] = k.tid == 0 ? 0 : -1;
+    for (int i = k.tid; i < WALK_MAX_BATCH / 32; i += NT) ws.mat[i] = 0u;
+    BScal rs;
+    bb_load<N, NT>(sm.root, rs, pool_of<N>(D), g, k);
+    const int root_color = gs[GS_COLOR];
+    u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
+    int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
+    const unsigned move_key = (unsigned)rs.moves;
+    const int root_last = (rs.moves >= 1 && rs.moves - 1 < G::MAXREC) ? hp[rs.moves - 1] : -1;
+    const size_t q = (size_t)g * D.cap;
+    const int nn0 = gs[GS_NNODES];
+    int nnodes = nn0, nleaf = 0, nuniq = 0, desc = gs[GS_DESC], rr = 1;
+    const bool prof = D.prof && g == 0 && k.tid == 0;
+    stage_wait();
+    k.sync();                                                // root rows (slot 0) are in shared memory
+    bool decided = false;                                    // is_move_decided (time_manager.py:146-163): visit counts only
+    {                                                        // change in the backup, so one evaluation serves the launch
+        const int nk = sm.st[0].hdr[H_K];
+        int top1 = 0;
+        for (int i = k.tid; i < nk; i += NT) top1 = max(top1, sm.st[0].vis[i]);
+        top1 = blk_max_i<N, NT>(sm, k, top1);
+        int nmax = 0, top2 = 0;
+        for (int i = k.tid; i < nk; i += NT) { const int v = sm.st[0].vis[i]; if (v == top1) nmax++; else top2 = max(top2, v); }
+        blk_sum_max<N, NT>(sm, k, nmax, top2);
+        if (nmax >= 2) top2 = top1;
+        const int remaining = visits - sm.st[0].hdr[H_NV];
+        const int cutoff = strict ? 0 : top1 - top2;
+        decided = remaining < cutoff;
+    }
+    bool fail = false;
+    for (int bi = 0; bi < batch && bi < WALK_MAX_BATCH; bi++) {
+        if (desc >= visits || (desc > 0 && decided)) { k.sync(); if (k.tid == 0) gs[GS_DONE] = 1; break; }
+        long long pt0 = prof ? clock64() : 0;
+        int color = root_color, cur = 0, plen = 0, slot = 0, m1 = root_last;
+        unsigned* path = D.path + (q + nleaf) * D.max_depth;
+        for (;;) {
+            Stage& st = slot_ptr(slot);
+            const int next = select_puct_blk<N, NT>(sm, st, D.cgos != 0, k, prof ? D.prof : nullptr);         // tree.py:213
+            if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
+            const size_t row = (size_t)cur * G::AP;
+            const int mv = st.action[next];
+            const int vl = st.vl[next], hvl = st.hdr[H_VL];
+            const int cv_before = st.vis[next] + vl;
+            int ci = st.cidx[next];
+            k.sync();                                        // every thread has read the edge before it changes
+            const bool coherent = slot == 0 || nc > 2;       // (with two slots, slot 1 is scratch: refetched on every use)
+            if (k.tid == 0) {
+                path[plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+                t.hdr[(size_t)cur * H_STRIDE + H_VL] = hvl + 1; t.cvl[row + next] = vl + 1;                  // :221 add_virtual_loss
+                if (coherent) { st.hdr[H_VL] = hvl + 1; st.vl[next] = vl + 1; }
+                ws.mv[plen] = (int16_t)mv;
+            }
+            plen++;
+            color = opp(color);
+            const int moves = rs.moves + plen;               // GoBoard.moves after this ply
+            int expand_threshold = 1;
+            if (moves > 2) {                                 // :224-229
+                if (moves - 1 >= G::MAXREC) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_HISTORY; fail = true; break; }
+                if (mv == PASS && m1 == PASS) expand_threshold = 10000000;
+            }
+            m1 = mv;
+            if (cv_before + 1 < expand_threshold + 1) {      // :231-241: this edge ends the descent
+                int flags = 0;
+                if (ci == NOT_EXPANDED) {                    // the node gets its index and its link now, its rows later
+                    if (nnodes >= D.tree.max_nodes) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_NODES; fail = true; break; }
+                    ci = nnodes++;
+                    if (k.tid == 0) {
+                        t.cidx[row + next] = ci;
+                        if (coherent) st.cidx[next] = ci;
+                        ws.newleaf[ci - nn0] = (int16_t)nleaf;
+                    }
+                    flags |= LEAF_EXPAND;
+                }
+                if (nleaf >= D.cap) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_QUEUE; fail = true; break; }
+                int dup_of = -1;
+                if (D.dedup) {                               // identical path among the earlier entries of this batch
+                    __threadfence_block();
+                    k.sync();
+                    int first = 0x7fffffff;
+                    for (int j = k.tid; j < nleaf; j += NT) {
+                        if (D.path_len[q + j] != plen) continue;
+                        const unsigned* pj = D.path + (q + j) * D.max_depth;
+                        bool same = true;
+                        for (int d = plen - 1; d >= 0 && same; d--) same = (pj[d] == path[d]);
+                        if (same) { first = j; break; }
+                    }
+                    first = blk_min_i<N, NT>(sm, k, first);
+                    if (first != 0x7fffffff) dup_of = first;
+                }
+                int lsl;
+                if (dup_of >= 0) lsl = ws.lslot[dup_of]; else { lsl = nuniq++; flags |= LEAF_SNAP; }
+                if (k.tid == 0) {
+                    D.path_len[q + nleaf] = plen; D.leaf_node[q + nleaf] = ci; D.leaf_slot[q + nleaf] = lsl;
+                    D.leaf_flag[q + nleaf] = (uint8_t)flags;
+                    ws.lslot[nleaf] = (int16_t)lsl; ws.lflag[nleaf] = (uint8_t)flags;
+                }
+                nleaf++;
+                if (nc == 2 && slot == 1 && k.tid == 0) ws.tag[1] = -1;
+                if (prof) D.prof[7]++;
+                break;
+            }
+            if (plen >= D.max_depth) { k.sync(); if (k.tid == 0) gs[GS_ERROR] |= ERR_DEPTH; fail = true; break; }
+            __threadfence_block();
+            k.sync();                                        // thread 0's updates (rows, ws.mv, tags) are visible
+            if (ci >= nn0 && !((ws.mat[(ci - nn0) >> 5] >> ((ci - nn0) & 31)) & 1u)) {
+                // a descent walks into a node allocated earlier in this launch: materialise it now (what the inline kernel
+                // does at every leaf): replay the path on the scratch board, fill the rows, write the snapshot
+                if (prof) pt0 = clock64();
+                bb_copy<N, NT>(sm.scratch, sm.root, k);
+                BScal s = rs;
+                int c = root_color;
+                for (int d = 0; d < plen; d++) { bb_put_stone<N, NT>(sm, sm.scratch, s, ws.mv[d], c, sm.zob, hh, hp, k); c = opp(c); }
+                expand_node_blk<N, NT>(sm, D, t, g, gs, sm.scratch, s, c, HistView{hh, hh, 0}, move_key, k, ci);
+                const int li = ws.newleaf[ci - nn0];
+                if (ws.lflag[li] & LEAF_SNAP) {
+                    const int prev = (s.moves - 1 < G::MAXREC) ? hp[s.moves - 1] : 0;
+                    write_snap_blk<N, NT>(D.snap + (q + ws.lslot[li]) * Snap<N>::BYTES, sm.scratch, prev, s.moves, c, k);
+                }
+                k.sync();
+                if (k.tid == 0) {
+                    ws.lflag[li] = 0; D.leaf_flag[q + li] = 0;
+                    ws.mat[(ci - nn0) >> 5] |= 1u << ((ci - nn0) & 31);
+                }
+                __threadfence_block();
+                k.sync();
+                if (prof) { const long long cc = clock64(); D.prof[3] += cc - pt0; pt0 = cc; D.prof[6]++; }
+            }
+            // the child's rows: cache hit, or one burst of asynchronous copies into the next victim slot
+            int hit = -1;
+            if (nc > 2) for (int sl = 1; sl < nc; sl++) if (ws.tag[sl] == ci) hit = sl;
+            if (hit < 0) {
+                if (prof) pt0 = clock64();
+                int victim = 1;
+                if (nc > 2) { victim = rr; if (victim == slot) victim = victim + 1 < nc ? victim + 1 : 1; rr = victim + 1 < nc ? victim + 1 : 1; }
+                stage_node<N, NT>(slot_ptr(victim), t, ci, k);
+                if (k.tid == 0) ws.tag[victim] = ci;
+                stage_wait();
+                k.sync();
+                hit = victim;
+                if (prof) { const long long cc = clock64(); D.prof[10] += cc - pt0; pt0 = cc; }
+            }
+            cur = ci; slot = hit;
+        }
+        __threadfence_block();
+        k.sync();
+        if (fail) break;
+        desc++;
+    }
+    if (k.tid == 0) { gs[GS_DESC] = desc; gs[GS_NLEAF] = nleaf; gs[GS_NUNIQ] = nuniq; gs[GS_NNODES] = nnodes; }
+}
+
+// The board half of a batch: one CTA per queued leaf (blockIdx.x) of every game (blockIdx.y).
+template <int N, int NT> struct ExpandSmem {
+    BlkSmem<N, NT> b;
+    u64 ph[Geo<N>::MAXREC];                                // position hashes of the descent's own moves
+    int16_t pp[Geo<N>::MAXREC];                            // ... and their points
+    int16_t mv[Geo<N>::MAXREC + 2];
+};
+
+template <int N, int NT>
+__global__ void __launch_bounds__(NT) k_expand_leaves_blk(Dev D, const uint32_t* __restrict__ eye2)
+{
+    using G = Geo<N>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ExpandSmem<N, NT>& es = *reinterpret_cast<ExpandSmem<N, NT>*>(smem_raw);
+    BlkSmem<N, NT>& sm = es.b;
+    Blk<NT> k;
+    const int g = blockIdx.y, i = blockIdx.x;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    if (i >= gs[GS_NLEAF]) return;
+    const size_t q = (size_t)g * D.cap;
+    const int flags = D.leaf_flag[q + i];
+    if (!flags) return;
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    const int plen = D.path_len[q + i];
+    const unsigned* path = D.path + (q + i) * D.max_depth;
+    for (int d = k.tid; d < plen; d += NT) {
+        const unsigned e = path[d];
+        es.mv[d] = t.action[(size_t)(e >> PATH_NODE_SHIFT) * G::AP + (e & ((1u << PATH_NODE_SHIFT) - 1))];
+    }
+    if (flags & LEAF_EXPAND)
+        for (int j = k.tid; j < 4096 / 4; j += NT) reinterpret_cast<uint4*>(sm.eye2)[j] = reinterpret_cast<const uint4*>(eye2)[j];
+    for (int j = k.tid; j < 4 * G::CELLS; j += NT) sm.zob[j] = D.zob[j];
+    BScal s;
+    bb_load<N, NT>(sm.root, s, pool_of<N>(D), g, k);
+    const int root_moves = s.moves;
+    int color = gs[GS_COLOR];
+    // the descent's record entries land in the private arrays: index `moves` of the game's record is ph[moves - root_moves]
+    u64* hh = es.ph - root_moves;
+    int16_t* hp = es.pp - root_moves;
+    for (int d = 0; d < plen; d++) { bb_put_stone<N, NT>(sm, sm.root, s, es.mv[d], color, sm.zob, hh, hp, k); color = opp(color); }
+    if (flags & LEAF_EXPAND)
+        expand_node_blk<N, NT>(sm, D, t, g, gs, sm.root, s, color, HistView{D.hist_hash + (size_t)g * G::MAXREC, es.ph, root_moves},
+                               (unsigned)root_moves, k, D.leaf_node[q + i]);
+    if (flags & LEAF_SNAP) {
+        const int prev = (s.moves - 1 < G::MAXREC) ? (s.moves - 1 >= root_moves ? hp[s.moves - 1] : D.hist_pos[(size_t)g * G::MAXREC + s.moves - 1]) : 0;
+        write_snap_blk<N, NT>(D.snap + (q + D.leaf_slot[q + i]) * Snap<N>::BYTES, sm.root, prev, s.moves, color, k);
+    }
 }
 
 // ---- process_mini_batch after the forward pass (tree.py:287-315) ----------------------------------------------------
@@ -698,43 +976,92 @@ __global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit)
                 t.cpol[(size_t)ni[u] * G::AP + c[u]] = (double)p;
             }
     }
-    // (b) tree.py:301-313 + node.py:118-138.  What the sequential walk needs from each leaf (backed-up value, path length,
-    //     the last 32 path entries) is fetched by the whole block first, so the walk itself only pays the node-pool updates.
+    // (b) tree.py:301-313 + node.py:118-138: every leaf adds its value to the edges and nodes of its path, leaf by leaf in
+    //     queue order -- the sums are fp32, so the ORDER of the additions into one accumulator is part of the result, but
+    //     different accumulators are independent.  The path entries of the batch are laid out leaf-major in shared memory;
+    //     the thread that owns the first entry of an edge (of a node) adds up all later entries of that edge (node) in order
+    //     and writes the accumulator once.  One thread per accumulator instead of one warp walking 256 leaves in sequence.
     extern __shared__ __align__(16) unsigned char bk_smem[];
-    constexpr int BK_MAX = 256;
+    constexpr int BK_MAX = 256, BK_ENT = 3072;
     float* s_val = reinterpret_cast<float*>(bk_smem);                            // [BK_MAX]
-    int* s_plen = reinterpret_cast<int*>(bk_smem + BK_MAX * 4);                  // [BK_MAX]
-    unsigned* s_path = reinterpret_cast<unsigned*>(bk_smem + BK_MAX * 8);        // [BK_MAX][32]
-    const bool staged = nl <= BK_MAX;
-    if (staged) {
+    int* s_off = reinterpret_cast<int*>(bk_smem + BK_MAX * 4);                   // [BK_MAX + 1]
+    unsigned* e_key = reinterpret_cast<unsigned*>(bk_smem + BK_MAX * 8 + 16);    // [BK_ENT]  node << PATH_NODE_SHIFT | child
+    unsigned* e_who = e_key + BK_ENT;                                            // [BK_ENT]  leaf << 16 | distance from the leaf
+    __shared__ int s_total;
+    if (warp == 0) {                                                             // exclusive scan of the path lengths
+        int run = 0;
+        for (int i0 = 0; i0 < nl && i0 < BK_MAX; i0 += 32) {
+            const int i = i0 + lane;
+            const int pl = i < nl ? D.path_len[q + i] : 0;
+            int inc = pl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            if (i < nl) s_off[i] = run + inc - pl;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) { s_total = run; if (nl <= BK_MAX) s_off[nl] = run; }
+    }
+    __syncthreads();
+    const int E = s_total;
+    if (nl <= BK_MAX && E <= BK_ENT) {
         for (int i = tid; i < nl; i += NT) {
             const float* v = D.value + (size_t)(slot0 + D.leaf_slot[q + i]) * 3;
             s_val[i] = __fadd_rn(v[0], __fmul_rn(v[1], 0.5f));                                                        // :303
-            s_plen[i] = D.path_len[q + i];
         }
-        for (int p = tid; p < nl * 32; p += NT) {
-            const int i = p >> 5, d = p & 31, plen = D.path_len[q + i];
-            s_path[p] = d < plen ? D.path[(q + i) * D.max_depth + plen - 1 - d] : 0u;
+        for (int i = warp; i < nl; i += NT / 32) {
+            const int o = s_off[i], plen = s_off[i + 1] - o;
+            const unsigned* path = D.path + (q + i) * D.max_depth;
+            for (int d = lane; d < plen; d += 32) { e_key[o + d] = path[plen - 1 - d]; e_who[o + d] = ((unsigned)i << 16) | (unsigned)d; }
         }
+        __syncthreads();
+        for (int e = tid; e < E; e += NT) {
+            const unsigned key = e_key[e], node = key >> PATH_NODE_SHIFT;
+            bool seen_edge = false, seen_node = false;
+            for (int j = 0; j < e && !(seen_edge && seen_node); j++) {
+                const unsigned kj = e_key[j];
+                seen_node |= (kj >> PATH_NODE_SHIFT) == node;
+                seen_edge |= kj == key;
+            }
+            if (seen_edge && seen_node) continue;
+            const size_t row = (size_t)node * G::AP;
+            const int c = (int)(key & ((1u << PATH_NODE_SHIFT) - 1));
+            int* h = t.hdr + (size_t)node * H_STRIDE;
+            float es = seen_edge ? 0.f : t.cvsum[row + c];
+            float hs = seen_node ? 0.f : __int_as_float(h[H_VSUM]);
+            int ec = 0, hc = 0; bool has0 = false; float last0 = 0.f;
+            for (int j = e; j < E; j++) {
+                const unsigned kj = e_key[j];
+                if ((kj >> PATH_NODE_SHIFT) != node) continue;
+                const unsigned who = e_who[j];
+                const int d = (int)(who & 0xffffu);
+                const float v0 = s_val[who >> 16];
+                const float v1 = __fsub_rn(1.0f, v0);
+                const float val = d == 0 ? v0 : ((d & 1) ? v1 : __fsub_rn(1.0f, v1));                                 // value = 1 - value per ply (:313)
+                if (!seen_node) { hs = __fadd_rn(hs, val); hc++; }
+                if (!seen_edge && kj == key) { es = __fadd_rn(es, val); ec++; if (d == 0) { has0 = true; last0 = v0; } }
+            }
+            if (!seen_edge) {
+                t.cvsum[row + c] = es; t.cvis[row + c] += ec; t.cvl[row + c] -= ec;
+                if (has0) t.cval[row + c] = last0;                                                                    // :308
+            }
+            if (!seen_node) { h[H_VSUM] = __float_as_int(hs); h[H_NV] += hc; h[H_VL] -= hc; }
+        }
+        if (tid == 0) { gs[GS_EVALS] += nl; gs[GS_UEVALS] += gs[GS_NUNIQ]; }
+        return;
     }
-    __syncthreads();
+    // fallback (very long paths): one warp walks the leaves in queue order
     if (warp != 0) return;
     for (int i = 0; i < nl; i++) {
-        float val0; int plen; unsigned e0;
-        if (staged) { val0 = s_val[i]; plen = s_plen[i]; e0 = s_path[i * 32 + lane]; }
-        else {
-            const float* v = D.value + (size_t)(slot0 + D.leaf_slot[q + i]) * 3;
-            val0 = __fadd_rn(v[0], __fmul_rn(v[1], 0.5f));
-            plen = D.path_len[q + i];
-            e0 = lane < plen ? D.path[(q + i) * D.max_depth + plen - 1 - lane] : 0u;
-        }
+        const float* v = D.value + (size_t)(slot0 + D.leaf_slot[q + i]) * 3;
+        const float val0 = __fadd_rn(v[0], __fmul_rn(v[1], 0.5f));
+        const int plen = D.path_len[q + i];
         if (plen > 0) {
             const unsigned* path = D.path + (q + i) * D.max_depth;
             const float val1 = __fsub_rn(1.0f, val0), val2 = __fsub_rn(1.0f, val1);
             for (int d0 = 0; d0 < plen; d0 += 32) {
                 const int d = d0 + lane;                                         // distance from the leaf
                 if (d < plen) {
-                    const unsigned e = d0 == 0 ? e0 : path[plen - 1 - d];
+                    const unsigned e = path[plen - 1 - d];
                     const int node = (int)(e >> PATH_NODE_SHIFT), c = (int)(e & ((1u << PATH_NODE_SHIFT) - 1));
                     const float val = d == 0 ? val0 : ((d & 1) ? val1 : val2);   // value = 1 - value per ply (:313)
                     const size_t row = (size_t)node * G::AP;

@@ -72,6 +72,8 @@ struct tg_engine {
     int sms = 148;
     bool puct_warp = false, unfused_planes = false;   // TG_UNFUSED_PLANES=1: k_planes + fp32 planes for the tensor-core evaluator too (A/B)
     int puct_nt = 256;                           // threads per game of the block-per-game PUCT kernels (128, 256 or 512)
+    bool puct_defer = false;                     // block-per-game batches: selections in one kernel, board work of all leaves in another
+    int walk_slots = 2;                          // node-row cache slots of k_walk_puct_blk
     const uint32_t* eye2 = nullptr;              // eye table packed to two bits per code (block-per-game kernels keep it in shared memory)
 };
 
@@ -159,7 +161,18 @@ template <int BN> static int setup_blk_attr()
     CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem<BN, 128>)));
     CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem<BN, 256>)));
     CK(cudaFuncSetAttribute(k_descend_puct_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlkSmem<BN, 512>)));
+    CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 128>)));
+    CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 256>)));
+    CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 512>)));
     return 0;
+}
+// shared memory of the tree-walk kernel with `slots` cached node rows
+template <int BN, int NT> static size_t walk_smem(int slots)
+{
+    return ((sizeof(WalkSmem<BN, NT>) + 15) & ~(size_t)15) + (size_t)(slots - 2) * sizeof(typename BlkSmem<BN, NT>::NodeStage);
 }
 template <int BN, int G> static int setup_tc_attr()
 {
@@ -264,6 +277,7 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     DA(D.gs, (size_t)games * GS_STRIDE); DA(D.game_id, games);
     DA(D.path, (size_t)games * e->path_words); DA(D.path_len, (size_t)games * e->cap_max);
     DA(D.leaf_node, (size_t)games * e->cap_max); DA(D.leaf_slot, (size_t)games * e->cap_max);
+    DA(D.leaf_flag, (size_t)games * e->cap_max);
     DA(D.snap, (size_t)games * e->cap_max * e->SNAP);
     DA(D.planes, (size_t)e->slot_cap * e->PLANES); DA(D.policy, (size_t)e->slot_cap * e->A); DA(D.value, (size_t)e->slot_cap * 3);
     DA(D.n_slots, 1); DA(D.slot_src, (size_t)e->slot_cap);
@@ -323,6 +337,13 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     e->unfused_planes = getenv("TG_UNFUSED_PLANES") != nullptr;
     e->puct_nt = games <= e->sms ? 512 : 256;
     if (const char* nt = getenv("TG_PUCT_NT")) e->puct_nt = atoi(nt);
+    // few games and real batches: the board work of a batch's leaves is spread over the idle SMs (tg_block.cuh, deferred
+    // expansion); TG_PUCT_DEFER=0/1 forces the choice (A/B measurements, tests)
+    e->puct_defer = games <= e->sms && e->cfg.batch_size >= 2;
+    if (const char* df = getenv("TG_PUCT_DEFER")) e->puct_defer = atoi(df) != 0;
+    if (e->cfg.batch_size > WALK_MAX_BATCH) e->puct_defer = false;
+    e->walk_slots = games <= e->sms ? 12 : 2;
+    if (const char* ws = getenv("TG_WALK_SLOTS")) e->walk_slots = std::min(16, std::max(2, atoi(ws)));
     {
         std::vector<uint8_t> tab; build_eye_table(tab);
         std::vector<uint32_t> packed(4096, 0u);
@@ -770,7 +791,14 @@ template <int BN> static int launch_eval(tg_engine* e, int use_logit, int max_sl
 template <int BN, int NT> static int puct_iter_blk(tg_engine* e, int visits, int batch, int strict, int max_slots, int* ev)
 {
     const Dev& D = e->D;
-    k_descend_puct_blk<BN, NT><<<D.games, NT, sizeof(BlkSmem<BN, NT>), e->stream>>>(D, e->eye2, visits, batch, strict);
+    if (e->puct_defer) {
+        int slots = e->walk_slots;
+        while (slots > 2 && walk_smem<BN, NT>(slots) > 227 * 1024) slots--;
+        k_walk_puct_blk<BN, NT><<<D.games, NT, walk_smem<BN, NT>(slots), e->stream>>>(D, e->eye2, visits, batch, strict, slots);
+        k_expand_leaves_blk<BN, NT><<<dim3(std::min(batch, D.cap), D.games), NT, sizeof(ExpandSmem<BN, NT>), e->stream>>>(D, e->eye2);
+        e->launches++;
+    } else
+        k_descend_puct_blk<BN, NT><<<D.games, NT, sizeof(BlkSmem<BN, NT>), e->stream>>>(D, e->eye2, visits, batch, strict);
     const int rc = launch_eval<BN>(e, 0, max_slots, ev);
     k_backup_blk<BN, NT><<<D.games, NT, 256 * 136, e->stream>>>(D, 0);
     return rc;

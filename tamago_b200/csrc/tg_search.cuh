@@ -45,6 +45,7 @@ struct Dev {
     int* path_len;           // [games][cap]
     int* leaf_node;          // [games][cap]  node whose priors the evaluation fills (-1: none)
     int* leaf_slot;          // [games][cap]  slot of the leaf relative to the game's slot base
+    uint8_t* leaf_flag;      // [games][cap]  deferred expansion (tg_block.cuh): what k_expand_leaves_blk still owes the leaf
     uint8_t* snap;           // [games][cap][Snap::BYTES]  one per unique slot
     // evaluator batch
     float* planes; float* policy; float* value; int* n_slots;

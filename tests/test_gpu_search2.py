@@ -96,7 +96,7 @@ def test_c4_full_games_19x19_puct400_vs_oracle(batch):
 
 
 def test_puct_kernel_variants_agree(monkeypatch):
-    """The three PUCT descent/backup kernels (warp per game; CTA per game with 256 or 512 threads) are bit-identical:
+    """The PUCT descent/backup kernels (warp per game; CTA per game with 256 or 512 threads, inline or deferred expansion) are bit-identical:
     160 positions (-> 256-thread CTAs by default), 100 (-> 512-thread CTAs) and the warp kernels forced by TG_PUCT_WARP,
     batch 1 and batch 16 (tentative priors, duplicate leaves), compared on every root statistic; a sample against the oracle."""
     import tamago_b200 as tb
@@ -114,11 +114,13 @@ def test_puct_kernel_variants_agree(monkeypatch):
             b.put_stone(pos, color); ml.append(pos); color = 3 - color
         boards.append((b, color)); mls.append(ml)
 
-    def run(ng, batch, visits, dedup, warp):
+    def run(ng, batch, visits, dedup, warp, env=()):
+        for key in ("TG_PUCT_WARP", "TG_PUCT_DEFER", "TG_WALK_SLOTS"):
+            monkeypatch.delenv(key, raising=False)
         if warp:
             monkeypatch.setenv("TG_PUCT_WARP", "1")
-        else:
-            monkeypatch.delenv("TG_PUCT_WARP", raising=False)
+        for key, val in env:
+            monkeypatch.setenv(key, val)
         e = tb.Engine(board_size=size, games=ng, max_visits=visits, superko=True, batch_size=batch, evaluator=tb.EVAL_HASHNET2,
                       dedup=dedup, seed=3)
         e.set_zobrist(zob)
@@ -136,13 +138,19 @@ def test_puct_kernel_variants_agree(monkeypatch):
 
     for batch, visits, dedup in ((1, 48, False), (16, 90, True)):
         ref = run(160, batch, visits, dedup, warp=True)
-        for ng in (160, 100):
-            got = run(ng, batch, visits, dedup, warp=False)
+        # block kernels: 256 / 512 threads; batches > 1 on <= 148 games split into tree walk + deferred expansion by default,
+        # forced on / off here, with the full node-row cache, a three-slot cache (evictions) and none
+        variants = [(160, ()), (100, ())]
+        if batch > 1:
+            variants += [(160, (("TG_PUCT_DEFER", "1"),)), (100, (("TG_PUCT_DEFER", "0"),)),
+                         (100, (("TG_WALK_SLOTS", "3"),)), (100, (("TG_WALK_SLOTS", "2"),))]
+        for ng, env in variants:
+            got = run(ng, batch, visits, dedup, warp=False, env=env)
             assert np.array_equal(got[0]["move"], ref[0]["move"][:ng]) and np.array_equal(got[0]["visits"], ref[0]["visits"][:ng])
             assert got[2] == ref[2][:ng]
             for a, b in zip(got[1], ref[1]):
                 for key in ("children_visits", "children_value_sum", "children_policy", "children_index", "children_virtual_loss"):
-                    assert np.array_equal(a[key], b[key]), (ng, batch, key)
+                    assert np.array_equal(a[key], b[key]), (ng, batch, key, env)
         for k in range(0, 160, 40):
             b, color = boards[k]
             t = orc.OracleTree(size, orc.hashnet2, tree_size=4096, batch_size=batch)
