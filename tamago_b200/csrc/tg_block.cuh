@@ -870,6 +870,296 @@ __global__ void __launch_bounds__(NT) k_walk_puct_blk(Dev D, const uint32_t* __r
     if (k.tid == 0) { gs[GS_DESC] = desc; gs[GS_NLEAF] = nleaf; gs[GS_NUNIQ] = nuniq; gs[GS_NNODES] = nnodes; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Wavefront tree walk: the descents of one batch as a software pipeline.
+//
+// Descent d+1 depends on descent d only through the nodes both visit, and it visits them one ply later: d changes a node
+// (virtual loss, child link) at the step it selects there and then moves DOWN.  So if every descent in flight advances one
+// ply per step and a new descent enters at the root each step, all descents in flight are at different depths -- different
+// nodes -- and every node still sees its visitors in descent order: the result is the sequential one, with up to NG plies
+// (and, more to the point, NG row fetches from L2) in flight at once.  A CTA of NT threads runs NG = NT / GT thread groups,
+// one descent each; three block barriers per step separate scoring, the group leaders' updates, and the row fetches.
+//
+// Two things are numbered in descent order but finish out of order (a shallow leaf of a later descent ends before a deep
+// earlier one): queue slots (= the descent's ordinal, known up front) and node indices of new leaves.  New nodes are
+// therefore linked with a provisional code (-2 - ordinal) and numbered after the walk, by a prefix count over the ordinals.
+// A descent that selects an edge carrying a provisional code has to enter a node that does not exist yet: it waits until
+// it is the oldest descent in flight (every older ordinal has ended, so the node's index is final), the younger descents
+// freeze behind it, and the whole CTA materialises the node (replay + expansion, as k_walk_puct_blk does).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int N, int NT, int GT> struct WaveSmem {
+    static constexpr int NG = NT / GT, GW = GT / 32;
+    BlkSmem<N, NT> b;
+    struct GState { int active, ord, cur, plen, color, m1, wait_ci, pad; } gst[NG];
+    u64 px[NG][GW]; int pi[NG][GW];                        // per-warp argmax partials of every group
+    int dec[NG];                                           // node whose rows the group fetches this step (-1: none)
+    int err;
+    int16_t mv[Geo<N>::MAXREC + 2];                        // moves of a path being materialised
+    int final_idx[WALK_MAX_BATCH];                         // node index of the leaf of every ordinal once it is final (-1 before)
+    uint8_t alloc[WALK_MAX_BATCH];                         // the descent of this ordinal allocated a node
+    // followed by (NG - 1) more NodeStage buffers in dynamic shared memory (group g > 0 uses buffer g - 1; group 0 b.st[1])
+};
+
+template <int N, int NT, int GT>
+__global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __restrict__ eye2, int visits, int batch, int strict)
+{
+    using G = Geo<N>;
+    using WS = WaveSmem<N, NT, GT>;
+    using Stage = typename BlkSmem<N, NT>::NodeStage;
+    constexpr int NG = WS::NG, GW = WS::GW, INF = 0x7fffffff;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WS& ws = *reinterpret_cast<WS*>(smem_raw);
+    BlkSmem<N, NT>& sm = ws.b;
+    Stage* extra = reinterpret_cast<Stage*>(smem_raw + ((sizeof(WS) + 15) & ~(size_t)15));
+    Blk<NT> k;
+    const int gi = k.tid / GT, gt = k.tid % GT, gw = gt >> 5;
+    Stage& gbuf = gi == 0 ? sm.st[1] : extra[gi - 1];
+    const int g = blockIdx.x;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    const bool idle = !gs[GS_ACTIVE] || gs[GS_FINISHED] || gs[GS_ERROR] || gs[GS_DONE];
+    k.sync();
+    if (k.tid == 0) { gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+    __threadfence_block();
+    k.sync();
+    if (idle) return;
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    stage_node<N, NT>(sm.st[0], t, 0, k);
+    for (int i = k.tid; i < 4096 / 4; i += NT) reinterpret_cast<uint4*>(sm.eye2)[i] = reinterpret_cast<const uint4*>(eye2)[i];
+    for (int i = k.tid; i < 4 * G::CELLS; i += NT) sm.zob[i] = D.zob[i];
+    for (int i = k.tid; i < WALK_MAX_BATCH; i += NT) { ws.final_idx[i] = -1; ws.alloc[i] = 0; }
+    if (k.tid < NG) { ws.gst[k.tid].active = 0; ws.gst[k.tid].wait_ci = -1; ws.gst[k.tid].ord = INF; ws.dec[k.tid] = -1; }
+    if (k.tid == 0) ws.err = 0;
+    BScal rs;
+    bb_load<N, NT>(sm.root, rs, pool_of<N>(D), g, k);
+    const int root_color = gs[GS_COLOR];
+    u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
+    int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
+    const unsigned move_key = (unsigned)rs.moves;
+    const int root_last = (rs.moves >= 1 && rs.moves - 1 < G::MAXREC) ? hp[rs.moves - 1] : -1;
+    const size_t q = (size_t)g * D.cap;
+    const int nn0 = gs[GS_NNODES], desc0 = gs[GS_DESC];
+    stage_wait();
+    k.sync();
+    int nd;                                                  // descents of this launch (tree.py:130-174 + is_move_decided)
+    {
+        const int nk = sm.st[0].hdr[H_K];
+        int top1 = 0;
+        for (int i = k.tid; i < nk; i += NT) top1 = max(top1, sm.st[0].vis[i]);
+        top1 = blk_max_i<N, NT>(sm, k, top1);
+        int nmax = 0, top2 = 0;
+        for (int i = k.tid; i < nk; i += NT) { const int v = sm.st[0].vis[i]; if (v == top1) nmax++; else top2 = max(top2, v); }
+        blk_sum_max<N, NT>(sm, k, nmax, top2);
+        if (nmax >= 2) top2 = top1;
+        const int remaining = visits - sm.st[0].hdr[H_NV];
+        const int cutoff = strict ? 0 : top1 - top2;
+        const bool decided = remaining < cutoff;
+        const int room = max(0, visits - desc0);
+        nd = min(min(batch, WALK_MAX_BATCH), room);
+        if (decided) nd = min(nd, desc0 == 0 ? 1 : 0);
+        nd = min(nd, D.cap);
+    }
+    const bool stops_early = nd < batch;                     // the sequential loop would hit its stop test inside this launch
+    // Group states live in shared memory, written only by the group's own leader in S2 (and by thread 0 inside the
+    // materialisation, behind barriers); what every thread has to agree on from one step to the next -- which group a new
+    // descent starts in, the stalled ordinal, the number of descents in flight -- is carried in registers.
+    int next_ord = nd > 0 ? 1 : 0, start_g = nd > 0 ? 0 : -1, stall_ord = INF, nact = nd > 0 ? 1 : 0;
+    k.sync();
+    const bool cgos = D.cgos != 0;
+    for (;;) {
+        // ---- S1: every running group scores the children of its node
+        if (nact == 0 && next_ord >= nd) break;
+        typename WS::GState me = ws.gst[gi];
+        const bool fresh = gi == start_g;
+        if (fresh) { me.active = 1; me.ord = next_ord - 1; me.cur = 0; me.plen = 0; me.color = root_color; me.m1 = root_last; me.wait_ci = -1; }
+        const bool run = me.active && me.wait_ci == -1 && me.ord < stall_ord;
+        const Stage& st = me.cur == 0 ? sm.st[0] : gbuf;
+        if (run) {
+            const int nk = st.hdr[H_K];
+            const double sq = sqrt((double)(st.hdr[H_NV] + st.hdr[H_VL] + 1));
+            double bv = 0.0; int bi = INF;
+            for (int i = gt; i < nk; i += GT) {              // node.py:141-157 + pucb.py:8-29, as select_puct_blk
+                const int cv = st.vis[i] + st.vl[i];
+                const double num = dmul(dmul(1.0, st.pol[i]), sq);
+                double v = num;
+                if (cv != 0) {
+                    const float vs = st.vsum[i];
+                    const double qv = vs == 0.0f ? 0.0 : ddiv((double)vs, (double)cv);
+                    const double u = num == 0.0 ? 0.0 : ddiv(num, (double)(cv + 1));
+                    v = dadd(qv, u);
+                }
+                if (cgos && i == nk - 1) v = dsub(v, 0.1);
+                if (bi == INF || v > bv) { bv = v; bi = i; }
+            }
+            u64 key = bi != INF ? order_key(bv) : 0ull;
+            warp_argmax_key(key, bi);
+            if (k.lane == 0) { ws.px[gi][gw] = key; ws.pi[gi][gw] = bi; }
+        }
+        k.sync();                                            // B1
+        // ---- S2: the group leader applies the ply
+        if (run) {
+            u64 k2 = k.lane < GW ? ws.px[gi][k.lane] : 0ull;
+            int next = k.lane < GW ? ws.pi[gi][k.lane] : INF;
+            warp_argmax_key(k2, next);
+            if (gt == 0) {
+                typename WS::GState& ms = ws.gst[gi];
+                if (fresh) ms = me;
+                const int cur = me.cur;
+                const size_t row = (size_t)cur * G::AP;
+                const int mv = st.action[next];
+                const int vl = st.vl[next], hvl = st.hdr[H_VL];
+                const int cv_before = st.vis[next] + vl;
+                int ci = st.cidx[next];
+                if (ci < -1 && ws.final_idx[-ci - 2] >= 0) ci = ws.final_idx[-ci - 2];   // (a copy fetched before the node was materialised)
+                unsigned* path = D.path + (q + me.ord) * D.max_depth;
+                path[me.plen] = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+                t.hdr[(size_t)cur * H_STRIDE + H_VL] = hvl + 1; t.cvl[row + next] = vl + 1;                  // :221 add_virtual_loss
+                if (cur == 0) { sm.st[0].hdr[H_VL] = hvl + 1; sm.st[0].vl[next] = vl + 1; }
+                const int plen = me.plen + 1;
+                const int moves = rs.moves + plen;
+                int expand_threshold = 1, dec = -1;
+                bool bad = false;
+                if (moves > 2) {                             // :224-229
+                    if (moves - 1 >= G::MAXREC) { atomicOr(&ws.err, ERR_HISTORY); bad = true; }
+                    if (mv == PASS && me.m1 == PASS) expand_threshold = 10000000;
+                }
+                if (bad) ms.active = 0;
+                else if (cv_before + 1 < expand_threshold + 1) {                  // :231-241: the edge ends the descent
+                    int flags = LEAF_SNAP;
+                    if (ci == NOT_EXPANDED) {
+                        ci = -2 - me.ord;                    // provisional: numbered after the walk
+                        t.cidx[row + next] = ci;
+                        if (cur == 0) sm.st[0].cidx[next] = ci;
+                        ws.alloc[me.ord] = 1;
+                        flags |= LEAF_EXPAND;
+                    }
+                    D.path_len[q + me.ord] = plen; D.leaf_node[q + me.ord] = ci; D.leaf_slot[q + me.ord] = me.ord;
+                    D.leaf_flag[q + me.ord] = (uint8_t)flags;
+                    ms.active = 0; ms.ord = INF;
+                } else if (plen >= D.max_depth) { atomicOr(&ws.err, ERR_DEPTH); ms.active = 0; }
+                else {
+                    ms.plen = plen; ms.color = opp(me.color); ms.m1 = mv;
+                    if (ci < -1) ms.wait_ci = ci;            // the child is a leaf of an earlier descent of this launch
+                    else { ms.cur = ci; dec = ci; }
+                }
+                ws.dec[gi] = dec;
+                __threadfence_block();
+            }
+        }
+        k.sync();                                            // B2
+        // ---- S3: row fetches, on-demand materialisation, the next descent enters
+        if (ws.err) break;
+        if (run && ws.dec[gi] >= 0) {
+            const int node = ws.dec[gi];
+            const size_t row = (size_t)node * G::AP;
+            for (int c = gt; c < G::AP / 4; c += GT) {
+                cp_async16(gbuf.vis + 4 * c, t.cvis + row + 4 * c);
+                cp_async16(gbuf.vl + 4 * c, t.cvl + row + 4 * c);
+                cp_async16(gbuf.vsum + 4 * c, t.cvsum + row + 4 * c);
+                cp_async16(gbuf.cidx + 4 * c, t.cidx + row + 4 * c);
+            }
+            for (int c = gt; c < G::AP / 2; c += GT) cp_async16(gbuf.pol + 2 * c, t.cpol + row + 2 * c);
+            for (int c = gt; c < G::AP / 8; c += GT) cp_async16(gbuf.action + 8 * c, t.action + row + 8 * c);
+            if (gt < H_STRIDE / 4) cp_async16(gbuf.hdr + 4 * gt, t.hdr + (size_t)node * H_STRIDE + 4 * gt);
+        }
+        stall_ord = INF; nact = 0; start_g = -1;
+        int first_free = -1, mg = -1, min_ord = INF;
+#pragma unroll
+        for (int j = NG - 1; j >= 0; j--) {
+            if (!ws.gst[j].active) { first_free = j; continue; }
+            nact++; min_ord = min(min_ord, ws.gst[j].ord);
+            if (ws.gst[j].wait_ci != -1 && ws.gst[j].ord < stall_ord) { stall_ord = ws.gst[j].ord; mg = j; }
+        }
+        if (stall_ord != INF && min_ord == stall_ord) {
+            // the waiting descent is the oldest in flight: the node it wants to enter gets its final index and its rows now
+            const int L = -ws.gst[mg].wait_ci - 2, ord = ws.gst[mg].ord, plen = ws.gst[mg].plen, c_at = ws.gst[mg].color;
+            int cnt = 0, dummy = 0;
+            for (int j = k.tid; j < L; j += NT) cnt += ws.alloc[j];
+            blk_sum_max<N, NT>(sm, k, cnt, dummy);
+            const int idx = nn0 + cnt;
+            const unsigned* path = D.path + (q + ord) * D.max_depth;
+            for (int d = k.tid; d < plen; d += NT) {
+                const unsigned e = path[d];
+                ws.mv[d] = t.action[(size_t)(e >> PATH_NODE_SHIFT) * G::AP + (e & ((1u << PATH_NODE_SHIFT) - 1))];
+            }
+            k.sync();
+            if (idx >= D.tree.max_nodes) { if (k.tid == 0) ws.err = ERR_NODES; k.sync(); break; }
+            bb_copy<N, NT>(sm.scratch, sm.root, k);
+            BScal s = rs;
+            int c = root_color;
+            for (int d = 0; d < plen; d++) { bb_put_stone<N, NT>(sm, sm.scratch, s, ws.mv[d], c, sm.zob, hh, hp, k); c = opp(c); }
+            expand_node_blk<N, NT>(sm, D, t, g, gs, sm.scratch, s, c_at, HistView{hh, hh, 0}, move_key, k, idx);
+            {
+                const int prev = (s.moves - 1 < G::MAXREC) ? hp[s.moves - 1] : 0;
+                write_snap_blk<N, NT>(D.snap + (q + L) * Snap<N>::BYTES, sm.scratch, prev, s.moves, c_at, k);
+            }
+            if (k.tid == 0) {
+                const unsigned e = path[plen - 1];
+                const int pnode = (int)(e >> PATH_NODE_SHIFT), pchild = (int)(e & ((1u << PATH_NODE_SHIFT) - 1));
+                t.cidx[(size_t)pnode * G::AP + pchild] = idx;
+                if (pnode == 0) sm.st[0].cidx[pchild] = idx;
+                D.leaf_node[q + L] = idx; D.leaf_flag[q + L] = 0;
+                ws.final_idx[L] = idx;
+                ws.gst[mg].cur = idx; ws.gst[mg].wait_ci = -1;
+                __threadfence_block();
+            }
+            k.sync();
+            if (gi == mg) {
+                const size_t row = (size_t)idx * G::AP;
+                for (int cc = gt; cc < G::AP / 4; cc += GT) {
+                    cp_async16(gbuf.vis + 4 * cc, t.cvis + row + 4 * cc);
+                    cp_async16(gbuf.vl + 4 * cc, t.cvl + row + 4 * cc);
+                    cp_async16(gbuf.vsum + 4 * cc, t.cvsum + row + 4 * cc);
+                    cp_async16(gbuf.cidx + 4 * cc, t.cidx + row + 4 * cc);
+                }
+                for (int cc = gt; cc < G::AP / 2; cc += GT) cp_async16(gbuf.pol + 2 * cc, t.cpol + row + 2 * cc);
+                for (int cc = gt; cc < G::AP / 8; cc += GT) cp_async16(gbuf.action + 8 * cc, t.action + row + 8 * cc);
+                if (gt < H_STRIDE / 4) cp_async16(gbuf.hdr + 4 * gt, t.hdr + (size_t)idx * H_STRIDE + 4 * gt);
+            }
+            stall_ord = INF;
+            for (int j = 0; j < NG; j++) if (j != mg && ws.gst[j].active && ws.gst[j].wait_ci != -1) stall_ord = min(stall_ord, ws.gst[j].ord);
+        }
+        if (stall_ord == INF && next_ord < nd && first_free >= 0) { start_g = first_free; next_ord++; nact++; }   // (its leader writes the state in S2)
+        stage_wait();
+        __threadfence_block();
+        k.sync();                                            // B3
+    }
+    stage_wait();
+    k.sync();
+    if (ws.err) {                                            // the game is dead: nothing of this launch is evaluated or backed up
+        if (k.tid == 0) { gs[GS_ERROR] |= ws.err; gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+        return;
+    }
+    // ---- node numbering in descent order, links of the new leaves, queue entries that refer to them
+    const int nleaf = next_ord;
+    int total = 0, dummy = 0;
+    for (int j = k.tid; j < nleaf; j += NT) total += ws.alloc[j];
+    blk_sum_max<N, NT>(sm, k, total, dummy);
+    if (nn0 + total > D.tree.max_nodes) {
+        if (k.tid == 0) { gs[GS_ERROR] |= ERR_NODES; gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+        return;
+    }
+    for (int j = k.tid; j < nleaf; j += NT) {
+        if (!ws.alloc[j] || ws.final_idx[j] >= 0) continue;
+        int cnt = 0;
+        for (int i = 0; i < j; i++) cnt += ws.alloc[i];
+        const int idx = nn0 + cnt;
+        ws.final_idx[j] = idx;
+        const int plen = D.path_len[q + j];
+        const unsigned e = D.path[(q + j) * D.max_depth + plen - 1];
+        t.cidx[(size_t)(e >> PATH_NODE_SHIFT) * G::AP + (e & ((1u << PATH_NODE_SHIFT) - 1))] = idx;
+    }
+    __threadfence_block();
+    k.sync();
+    for (int j = k.tid; j < nleaf; j += NT) {
+        const int ln = D.leaf_node[q + j];
+        if (ln < -1) D.leaf_node[q + j] = ws.final_idx[-ln - 2];
+    }
+    if (k.tid == 0) {
+        gs[GS_DESC] = desc0 + nleaf; gs[GS_NLEAF] = nleaf; gs[GS_NUNIQ] = nleaf; gs[GS_NNODES] = nn0 + total;
+        if (stops_early) gs[GS_DONE] = 1;
+    }
+}
+
 // The board half of a batch: one CTA per queued leaf (blockIdx.x) of every game (blockIdx.y).
 template <int N, int NT> struct ExpandSmem {
     BlkSmem<N, NT> b;
@@ -923,8 +1213,34 @@ __global__ void __launch_bounds__(NT) k_expand_leaves_blk(Dev D, const uint32_t*
 // (a) priors / raw value of every evaluated node: all (leaf, child) pairs are independent and are spread over the
 //     whole block with several loads in flight per thread; (b) values: one warp walks the leaves in queue order (fp32
 //     sums depend on it) with the next leaf's path entries already in flight.
+// Part (a) alone, one CTA per evaluated leaf (blockIdx.x) of every game (blockIdx.y): with a handful of games the priors of
+// a 256-leaf batch are the larger half of the backup, and every (leaf, child) pair is independent.
+template <int N>
+__global__ void __launch_bounds__(128) k_backup_priors_blk(Dev D, int use_logit)
+{
+    using G = Geo<N>;
+    const int g = blockIdx.y, i = blockIdx.x;
+    const int* gs = D.gs + (size_t)g * GS_STRIDE;
+    if (i >= gs[GS_NLEAF]) return;
+    const size_t q = (size_t)g * D.cap;
+    const int slot = gs[GS_SLOT0] + D.leaf_slot[q + i];
+    const int ni = D.leaf_node[q + i];
+    if (slot >= D.slot_cap || ni < 0) return;                                    // (k_backup_blk reports the overflow)
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    const float* v = D.value + (size_t)slot * 3;
+    const float* pol = D.policy + (size_t)slot * G::A;
+    if (threadIdx.x == 0) t.hdr[(size_t)ni * H_STRIDE + H_RAW] = __float_as_int(__fadd_rn(__fmul_rn(v[1], 0.5f), v[2]));  // tree.py:300
+    const int nk = t.hdr[(size_t)ni * H_STRIDE + H_K];
+    for (int c = threadIdx.x; c < nk; c += 128) {                                // node.py:86-93, tree.py:287-299
+        const int a = t.action[(size_t)ni * G::AP + c];
+        float p = a == PASS ? pol[G::NN] : pol[(a / G::W - 1) * N + (a % G::W - 1)];
+        if (a == PASS && use_logit) p = __fsub_rn(p, 0.5f);                                                           // tree.py:292-294
+        t.cpol[(size_t)ni * G::AP + c] = (double)p;
+    }
+}
+
 template <int N, int NT>
-__global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit)
+__global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit, int priors_done)
 {
     using G = Geo<N>;
     const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -941,7 +1257,7 @@ __global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit)
         const int slot = slot0 + D.leaf_slot[q + i];
         if (slot >= D.slot_cap) { bad = 1; continue; }
         const int ni = D.leaf_node[q + i];
-        if (ni >= 0) {
+        if (ni >= 0 && !priors_done) {
             const float* v = D.value + (size_t)slot * 3;
             t.hdr[(size_t)ni * H_STRIDE + H_RAW] = __float_as_int(__fadd_rn(__fmul_rn(v[1], 0.5f), v[2]));           // tree.py:300
         }
@@ -949,7 +1265,7 @@ __global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit)
     __syncthreads();
     if (bad) { if (tid == 0) gs[GS_ERROR] |= ERR_QUEUE; return; }
     constexpr int U = 4;
-    for (int p0 = tid; p0 < nl * G::AP; p0 += NT * U) {                          // node.py:86-93, tree.py:287-299
+    for (int p0 = tid; p0 < nl * G::AP && !priors_done; p0 += NT * U) {          // node.py:86-93, tree.py:287-299
         int ni[U], c[U], a[U]; const float* pol[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {

@@ -74,6 +74,8 @@ struct tg_engine {
     int puct_nt = 256;                           // threads per game of the block-per-game PUCT kernels (128, 256 or 512)
     bool puct_defer = false;                     // block-per-game batches: selections in one kernel, board work of all leaves in another
     int walk_slots = 2;                          // node-row cache slots of k_walk_puct_blk
+    bool puct_wave = false;                      // deferred mode: the tree walk runs as a wavefront (k_wave_puct_blk)
+    int wave_gt = 128;                           // threads per descent of the wavefront walk (512-thread CTAs: 128 measured faster than 64)
     const uint32_t* eye2 = nullptr;              // eye table packed to two bits per code (block-per-game kernels keep it in shared memory)
 };
 
@@ -155,6 +157,16 @@ template <int BN> static int setup_kernel_attrs()
     CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return 0;
 }
+template <int BN, int NT, int GT> static size_t wave_smem()
+{
+    return ((sizeof(WaveSmem<BN, NT, GT>) + 15) & ~(size_t)15) + (size_t)(NT / GT - 1) * sizeof(typename BlkSmem<BN, NT>::NodeStage);
+}
+template <int BN, int NT, int GT> static int setup_wave_attr()
+{
+    static_assert(sizeof(WaveSmem<BN, NT, GT>) + (NT / GT) * sizeof(typename BlkSmem<BN, NT>::NodeStage) <= 227 * 1024, "wavefront walk scratch");
+    CK(cudaFuncSetAttribute(k_wave_puct_blk<BN, NT, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem<BN, NT, GT>()));
+    return 0;
+}
 template <int BN> static int setup_blk_attr()
 {
     static_assert(sizeof(BlkSmem<BN, 512>) <= 96 * 1024, "block-per-game scratch");
@@ -164,6 +176,7 @@ template <int BN> static int setup_blk_attr()
     CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (setup_wave_attr<BN, 512, 64>() || setup_wave_attr<BN, 512, 128>() || setup_wave_attr<BN, 256, 64>() || setup_wave_attr<BN, 128, 32>()) return -1;
     CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 128>)));
     CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 256>)));
     CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 512>)));
@@ -342,6 +355,11 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     e->puct_defer = games <= e->sms && e->cfg.batch_size >= 2;
     if (const char* df = getenv("TG_PUCT_DEFER")) e->puct_defer = atoi(df) != 0;
     if (e->cfg.batch_size > WALK_MAX_BATCH) e->puct_defer = false;
+    // ... and the walk itself is pipelined over the descents of the batch (leaf deduplication needs the queue in order:
+    // sequential walk); TG_PUCT_WAVE=0/1, TG_WAVE_GT=64/128 (512-thread CTAs) for A/B measurements
+    e->puct_wave = e->puct_defer && !e->cfg.dedup;
+    if (const char* wv = getenv("TG_PUCT_WAVE")) e->puct_wave = e->puct_defer && !e->cfg.dedup && atoi(wv) != 0;
+    if (const char* gt = getenv("TG_WAVE_GT")) e->wave_gt = atoi(gt) == 64 ? 64 : 128;
     e->walk_slots = games <= e->sms ? 12 : 2;
     if (const char* ws = getenv("TG_WALK_SLOTS")) e->walk_slots = std::min(16, std::max(2, atoi(ws)));
     {
@@ -791,7 +809,14 @@ template <int BN> static int launch_eval(tg_engine* e, int use_logit, int max_sl
 template <int BN, int NT> static int puct_iter_blk(tg_engine* e, int visits, int batch, int strict, int max_slots, int* ev)
 {
     const Dev& D = e->D;
-    if (e->puct_defer) {
+    if (e->puct_defer && e->puct_wave) {
+        if (NT == 512 && e->wave_gt == 128)
+            k_wave_puct_blk<BN, NT, (NT == 512 ? 128 : NT / 4)><<<D.games, NT, wave_smem<BN, NT, (NT == 512 ? 128 : NT / 4)>(), e->stream>>>(D, e->eye2, visits, batch, strict);
+        else
+            k_wave_puct_blk<BN, NT, (NT == 512 ? 64 : NT / 4)><<<D.games, NT, wave_smem<BN, NT, (NT == 512 ? 64 : NT / 4)>(), e->stream>>>(D, e->eye2, visits, batch, strict);
+        k_expand_leaves_blk<BN, NT><<<dim3(std::min(batch, D.cap), D.games), NT, sizeof(ExpandSmem<BN, NT>), e->stream>>>(D, e->eye2);
+        e->launches++;
+    } else if (e->puct_defer) {
         int slots = e->walk_slots;
         while (slots > 2 && walk_smem<BN, NT>(slots) > 227 * 1024) slots--;
         k_walk_puct_blk<BN, NT><<<D.games, NT, walk_smem<BN, NT>(slots), e->stream>>>(D, e->eye2, visits, batch, strict, slots);
@@ -800,7 +825,8 @@ template <int BN, int NT> static int puct_iter_blk(tg_engine* e, int visits, int
     } else
         k_descend_puct_blk<BN, NT><<<D.games, NT, sizeof(BlkSmem<BN, NT>), e->stream>>>(D, e->eye2, visits, batch, strict);
     const int rc = launch_eval<BN>(e, 0, max_slots, ev);
-    k_backup_blk<BN, NT><<<D.games, NT, 256 * 136, e->stream>>>(D, 0);
+    if (e->puct_defer) { k_backup_priors_blk<BN><<<dim3(std::min(batch, D.cap), D.games), 128, 0, e->stream>>>(D, 0); e->launches++; }
+    k_backup_blk<BN, NT><<<D.games, NT, 256 * 136, e->stream>>>(D, 0, e->puct_defer ? 1 : 0);
     return rc;
 }
 

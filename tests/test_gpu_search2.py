@@ -115,7 +115,7 @@ def test_puct_kernel_variants_agree(monkeypatch):
         boards.append((b, color)); mls.append(ml)
 
     def run(ng, batch, visits, dedup, warp, env=()):
-        for key in ("TG_PUCT_WARP", "TG_PUCT_DEFER", "TG_WALK_SLOTS"):
+        for key in ("TG_PUCT_WARP", "TG_PUCT_DEFER", "TG_WALK_SLOTS", "TG_PUCT_WAVE", "TG_WAVE_GT"):
             monkeypatch.delenv(key, raising=False)
         if warp:
             monkeypatch.setenv("TG_PUCT_WARP", "1")
@@ -136,14 +136,16 @@ def test_puct_kernel_variants_agree(monkeypatch):
         e.close()
         return res, roots, sizes
 
-    for batch, visits, dedup in ((1, 48, False), (16, 90, True)):
+    for batch, visits, dedup in ((1, 48, False), (16, 90, True), (16, 90, False)):
         ref = run(160, batch, visits, dedup, warp=True)
         # block kernels: 256 / 512 threads; batches > 1 on <= 148 games split into tree walk + deferred expansion by default,
         # forced on / off here, with the full node-row cache, a three-slot cache (evictions) and none
+        # and the walk either pipelined over the descents (wavefront; not with leaf deduplication) or sequential
         variants = [(160, ()), (100, ())]
         if batch > 1:
-            variants += [(160, (("TG_PUCT_DEFER", "1"),)), (100, (("TG_PUCT_DEFER", "0"),)),
-                         (100, (("TG_WALK_SLOTS", "3"),)), (100, (("TG_WALK_SLOTS", "2"),))]
+            variants += [(160, (("TG_PUCT_DEFER", "1"),)), (100, (("TG_PUCT_DEFER", "0"),)), (100, (("TG_WAVE_GT", "64"),)),
+                         (100, (("TG_PUCT_WAVE", "0"),)), (100, (("TG_PUCT_WAVE", "0"), ("TG_WALK_SLOTS", "3"))),
+                         (100, (("TG_PUCT_WAVE", "0"), ("TG_WALK_SLOTS", "2")))]
         for ng, env in variants:
             got = run(ng, batch, visits, dedup, warp=False, env=env)
             assert np.array_equal(got[0]["move"], ref[0]["move"][:ng]) and np.array_equal(got[0]["visits"], ref[0]["visits"][:ng])
