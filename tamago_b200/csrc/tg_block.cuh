@@ -901,7 +901,7 @@ template <int N, int NT, int GT> struct WaveSmem {
 };
 
 template <int N, int NT, int GT>
-__global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __restrict__ eye2, int visits, int batch, int strict)
+__global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __restrict__ eye2, int visits, int batch, int strict, int nsqrt)
 {
     using G = Geo<N>;
     using WS = WaveSmem<N, NT, GT>;
@@ -911,7 +911,9 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
     WS& ws = *reinterpret_cast<WS*>(smem_raw);
     BlkSmem<N, NT>& sm = ws.b;
     Stage* extra = reinterpret_cast<Stage*>(smem_raw + ((sizeof(WS) + 15) & ~(size_t)15));
-    Blk<NT> k;
+    double* sqtab = reinterpret_cast<double*>(extra + (NG - 1));      // sqrt(n), n < nsqrt: one table per launch instead of a
+    Blk<NT> k;                                                        // ~450-cycle float64 square root per thread and ply
+    for (int i = threadIdx.x; i < nsqrt; i += NT) sqtab[i] = sqrt((double)i);
     const int gi = k.tid / GT, gt = k.tid % GT, gw = gt >> 5;
     Stage& gbuf = gi == 0 ? sm.st[1] : extra[gi - 1];
     const int g = blockIdx.x;
@@ -922,6 +924,8 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
     __threadfence_block();
     k.sync();
     if (idle) return;
+    const bool prof = D.prof && g == 0 && k.tid == 0;
+    const long long pk0 = prof ? clock64() : 0;
     const Tree t = tree_of<G::AP>(D.tree, g);
     stage_node<N, NT>(sm.st[0], t, 0, k);
     for (int i = k.tid; i < 4096 / 4; i += NT) reinterpret_cast<uint4*>(sm.eye2)[i] = reinterpret_cast<const uint4*>(eye2)[i];
@@ -964,10 +968,13 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
     // descent starts in, the stalled ordinal, the number of descents in flight -- is carried in registers.
     int next_ord = nd > 0 ? 1 : 0, start_g = nd > 0 ? 0 : -1, stall_ord = INF, nact = nd > 0 ? 1 : 0;
     k.sync();
+    long long pr[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // clock64 accumulators of thread 0 (registers; flushed at the end)
+    if (prof) pr[0] = clock64() - pk0;
     const bool cgos = D.cgos != 0;
     for (;;) {
         // ---- S1: every running group scores the children of its node
         if (nact == 0 && next_ord >= nd) break;
+        long long pt0 = prof ? clock64() : 0;
         typename WS::GState me = ws.gst[gi];
         const bool fresh = gi == start_g;
         if (fresh) { me.active = 1; me.ord = next_ord - 1; me.cur = 0; me.plen = 0; me.color = root_color; me.m1 = root_last; me.wait_ci = -1; }
@@ -975,31 +982,84 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
         const Stage& st = me.cur == 0 ? sm.st[0] : gbuf;
         if (run) {
             const int nk = st.hdr[H_K];
-            const double sq = sqrt((double)(st.hdr[H_NV] + st.hdr[H_VL] + 1));
-            double bv = 0.0; int bi = INF;
-            for (int i = gt; i < nk; i += GT) {              // node.py:141-157 + pucb.py:8-29, as select_puct_blk
-                const int cv = st.vis[i] + st.vl[i];
-                const double num = dmul(dmul(1.0, st.pol[i]), sq);
-                double v = num;
-                if (cv != 0) {
-                    const float vs = st.vsum[i];
-                    const double qv = vs == 0.0f ? 0.0 : ddiv((double)vs, (double)cv);
-                    const double u = num == 0.0 ? 0.0 : ddiv(num, (double)(cv + 1));
-                    v = dadd(qv, u);
+            const int nsq = st.hdr[H_NV] + st.hdr[H_VL] + 1;                  // pucb.py:16
+            const double sq = nsq < nsqrt ? sqtab[nsq] : sqrt((double)nsq);
+            // node.py:141-157 + pucb.py:8-29, the arithmetic of select_puct_blk per child.  The walk is bound by the SM's float64
+            // issue rate (measured: ~1 warp instruction per cycle per SM), so float64 work is what is trimmed: the square root
+            // comes from the group leader (ws.sq), 1.0 * prior is the prior, and a warp none of whose 32 children has been
+            // visited skips both correctly rounded divisions (~24 float64 instructions) -- below the root that is most warps.
+            constexpr int CHG = (G::A + GT - 1) / GT;
+            double vv[CHG];
+            int cvs[CHG];
+            bool redo = false, anyv = false;                 // redo: an operand outside the fast division's range (a prior below 2^-120)
+#pragma unroll
+            for (int c = 0; c < CHG; c++) {
+                const int i = gt + c * GT;
+                const bool valid = i < nk;
+                cvs[c] = valid ? st.vis[i] + st.vl[i] : 0;
+                vv[c] = dmul(valid ? st.pol[i] : 0.0, sq);   // (1.0 * prior) * sqrt(...): the first product is exact
+                anyv |= cvs[c] != 0;
+            }
+            if (prof) { const long long c = clock64(); pr[2] += c - pt0; pr[6]++; }
+            if (__any_sync(0xffffffffu, anyv)) {
+                // all divisions of the thread's children as ONE straight-line block (ddiv_fast has no branch): 2 * CHG
+                // independent ~250-cycle chains that the scheduler interleaves
+#pragma unroll
+                for (int c = 0; c < CHG; c++) {
+                    const int i = gt + c * GT;
+                    const bool has = cvs[c] != 0;
+                    const float vs = has ? st.vsum[i] : 0.f;
+                    const double num = vv[c];
+                    const bool hq = has && vs != 0.0f;       // 0 / x = +0 exactly: no division
+                    const bool hu = has && num != 0.0;
+                    bool sq_, su_;
+                    const double qd = ddiv_fast(hq ? (double)vs : 1.0, has ? (double)cvs[c] : 1.0, sq_);
+                    const double ud = ddiv_fast(hu ? num : 1.0, (double)(cvs[c] + 1), su_);
+                    if (has) vv[c] = dadd(hq ? qd : 0.0, hu ? ud : 0.0);
+                    redo |= (hq && sq_) || (hu && su_);
                 }
-                if (cgos && i == nk - 1) v = dsub(v, 0.1);
-                if (bi == INF || v > bv) { bv = v; bi = i; }
+            }
+            if (cgos && nk >= 1 && (nk - 1) % GT == gt) {
+#pragma unroll
+                for (int c = 0; c < CHG; c++) if (gt + c * GT == nk - 1) vv[c] = dsub(vv[c], 0.1);
+            }
+            if (prof) pr[3] += clock64() - pt0;
+            if (redo) {                                      // rare: the library division for this thread's children
+                for (int c = 0; c < CHG; c++) {
+                    const int i = gt + c * GT;
+                    if (i >= nk) continue;
+                    const int cv = st.vis[i] + st.vl[i];
+                    const double num = dmul(st.pol[i], sq);
+                    double v = num;
+                    if (cv != 0) {
+                        const float vs = st.vsum[i];
+                        const double qv = vs == 0.0f ? 0.0 : ddiv((double)vs, (double)cv);
+                        const double u = num == 0.0 ? 0.0 : ddiv(num, (double)(cv + 1));
+                        v = dadd(qv, u);
+                    }
+                    if (cgos && i == nk - 1) v = dsub(v, 0.1);
+                    vv[c] = v;
+                }
+            }
+            double bv = 0.0; int bi = INF;
+#pragma unroll
+            for (int c = 0; c < CHG; c++) {
+                const int i = gt + c * GT;
+                if (i < nk && (bi == INF || vv[c] > bv)) { bv = vv[c]; bi = i; }
             }
             u64 key = bi != INF ? order_key(bv) : 0ull;
             warp_argmax_key(key, bi);
             if (k.lane == 0) { ws.px[gi][gw] = key; ws.pi[gi][gw] = bi; }
+            if (prof) pr[4] += clock64() - pt0;
         }
         k.sync();                                            // B1
+        if (prof) { const long long c = clock64(); pr[8] += c - pt0; pt0 = c; pr[5]++; }
         // ---- S2: the group leader applies the ply
         if (run) {
             u64 k2 = k.lane < GW ? ws.px[gi][k.lane] : 0ull;
             int next = k.lane < GW ? ws.pi[gi][k.lane] : INF;
             warp_argmax_key(k2, next);
+            if (prof) pr[7] += clock64() - pt0;
             if (gt == 0) {
                 typename WS::GState& ms = ws.gst[gi];
                 if (fresh) ms = me;
@@ -1041,11 +1101,12 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
                     if (ci < -1) ms.wait_ci = ci;            // the child is a leaf of an earlier descent of this launch
                     else { ms.cur = ci; dec = ci; }
                 }
-                ws.dec[gi] = dec;
-                __threadfence_block();
-            }
+                if (prof) pr[11] += clock64() - pt0;
+                ws.dec[gi] = dec;                            // (no fence: the block barrier that follows orders these writes, global
+            }                                                //  ones included, before every later access of the CTA)
         }
         k.sync();                                            // B2
+        if (prof) { const long long c = clock64(); pr[9] += c - pt0; pt0 = c; }
         // ---- S3: row fetches, on-demand materialisation, the next descent enters
         if (ws.err) break;
         if (run && ws.dec[gi] >= 0) {
@@ -1120,8 +1181,8 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
         }
         if (stall_ord == INF && next_ord < nd && first_free >= 0) { start_g = first_free; next_ord++; nact++; }   // (its leader writes the state in S2)
         stage_wait();
-        __threadfence_block();
         k.sync();                                            // B3
+        if (prof) { const long long c = clock64(); pr[10] += c - pt0; pr[1] += nact; }
     }
     stage_wait();
     k.sync();
@@ -1158,6 +1219,7 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
         gs[GS_DESC] = desc0 + nleaf; gs[GS_NLEAF] = nleaf; gs[GS_NUNIQ] = nleaf; gs[GS_NNODES] = nn0 + total;
         if (stops_early) gs[GS_DONE] = 1;
     }
+    if (prof) for (int i = 0; i < 12; i++) D.prof[i] += pr[i];
 }
 
 // The board half of a batch: one CTA per queued leaf (blockIdx.x) of every game (blockIdx.y).

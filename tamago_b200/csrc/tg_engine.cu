@@ -75,6 +75,7 @@ struct tg_engine {
     bool puct_defer = false;                     // block-per-game batches: selections in one kernel, board work of all leaves in another
     int walk_slots = 2;                          // node-row cache slots of k_walk_puct_blk
     bool puct_wave = false;                      // deferred mode: the tree walk runs as a wavefront (k_wave_puct_blk)
+    int wave_nt = 512;                           // CTA size of the wavefront walk when the other block kernels use 512 threads
     int wave_gt = 128;                           // threads per descent of the wavefront walk (512-thread CTAs: 128 measured faster than 64)
     const uint32_t* eye2 = nullptr;              // eye table packed to two bits per code (block-per-game kernels keep it in shared memory)
 };
@@ -157,13 +158,14 @@ template <int BN> static int setup_kernel_attrs()
     CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return 0;
 }
-template <int BN, int NT, int GT> static size_t wave_smem()
+constexpr int WAVE_SQRT_MAX = 4096;             // entries of the wavefront walk's square-root table (larger arguments are computed)
+template <int BN, int NT, int GT> static size_t wave_smem(int nsqrt = WAVE_SQRT_MAX)
 {
-    return ((sizeof(WaveSmem<BN, NT, GT>) + 15) & ~(size_t)15) + (size_t)(NT / GT - 1) * sizeof(typename BlkSmem<BN, NT>::NodeStage);
+    return ((sizeof(WaveSmem<BN, NT, GT>) + 15) & ~(size_t)15) + (size_t)(NT / GT - 1) * sizeof(typename BlkSmem<BN, NT>::NodeStage) + (size_t)nsqrt * 8;
 }
 template <int BN, int NT, int GT> static int setup_wave_attr()
 {
-    static_assert(sizeof(WaveSmem<BN, NT, GT>) + (NT / GT) * sizeof(typename BlkSmem<BN, NT>::NodeStage) <= 227 * 1024, "wavefront walk scratch");
+    static_assert(sizeof(WaveSmem<BN, NT, GT>) + (NT / GT) * sizeof(typename BlkSmem<BN, NT>::NodeStage) + WAVE_SQRT_MAX * 8 <= 227 * 1024, "wavefront walk scratch");
     CK(cudaFuncSetAttribute(k_wave_puct_blk<BN, NT, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem<BN, NT, GT>()));
     return 0;
 }
@@ -176,7 +178,7 @@ template <int BN> static int setup_blk_attr()
     CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (setup_wave_attr<BN, 512, 64>() || setup_wave_attr<BN, 512, 128>() || setup_wave_attr<BN, 256, 64>() || setup_wave_attr<BN, 128, 32>()) return -1;
+    if (setup_wave_attr<BN, 1024, 128>() || setup_wave_attr<BN, 512, 64>() || setup_wave_attr<BN, 512, 128>() || setup_wave_attr<BN, 256, 64>() || setup_wave_attr<BN, 128, 32>()) return -1;
     CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 128>)));
     CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 256>)));
     CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 512>)));
@@ -359,6 +361,7 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     // sequential walk); TG_PUCT_WAVE=0/1, TG_WAVE_GT=64/128 (512-thread CTAs) for A/B measurements
     e->puct_wave = e->puct_defer && !e->cfg.dedup;
     if (const char* wv = getenv("TG_PUCT_WAVE")) e->puct_wave = e->puct_defer && !e->cfg.dedup && atoi(wv) != 0;
+    if (const char* wn = getenv("TG_WAVE_NT")) e->wave_nt = atoi(wn) == 1024 ? 1024 : 512;
     if (const char* gt = getenv("TG_WAVE_GT")) e->wave_gt = atoi(gt) == 64 ? 64 : 128;
     e->walk_slots = games <= e->sms ? 12 : 2;
     if (const char* ws = getenv("TG_WALK_SLOTS")) e->walk_slots = std::min(16, std::max(2, atoi(ws)));
@@ -810,10 +813,13 @@ template <int BN, int NT> static int puct_iter_blk(tg_engine* e, int visits, int
 {
     const Dev& D = e->D;
     if (e->puct_defer && e->puct_wave) {
-        if (NT == 512 && e->wave_gt == 128)
-            k_wave_puct_blk<BN, NT, (NT == 512 ? 128 : NT / 4)><<<D.games, NT, wave_smem<BN, NT, (NT == 512 ? 128 : NT / 4)>(), e->stream>>>(D, e->eye2, visits, batch, strict);
+        const int nsq = std::min(WAVE_SQRT_MAX, visits + batch + 2);              // sqrt table: visits + virtual losses + 1 of any node
+        if (NT == 512 && e->wave_gt == 128 && e->wave_nt == 1024)     // eight descents in flight, 128 threads each
+            k_wave_puct_blk<BN, 1024, 128><<<D.games, 1024, wave_smem<BN, 1024, 128>(nsq), e->stream>>>(D, e->eye2, visits, batch, strict, nsq);
+        else if (NT == 512 && e->wave_gt == 128)
+            k_wave_puct_blk<BN, NT, (NT == 512 ? 128 : NT / 4)><<<D.games, NT, wave_smem<BN, NT, (NT == 512 ? 128 : NT / 4)>(nsq), e->stream>>>(D, e->eye2, visits, batch, strict, nsq);
         else
-            k_wave_puct_blk<BN, NT, (NT == 512 ? 64 : NT / 4)><<<D.games, NT, wave_smem<BN, NT, (NT == 512 ? 64 : NT / 4)>(), e->stream>>>(D, e->eye2, visits, batch, strict);
+            k_wave_puct_blk<BN, NT, (NT == 512 ? 64 : NT / 4)><<<D.games, NT, wave_smem<BN, NT, (NT == 512 ? 64 : NT / 4)>(nsq), e->stream>>>(D, e->eye2, visits, batch, strict, nsq);
         k_expand_leaves_blk<BN, NT><<<dim3(std::min(batch, D.cap), D.games), NT, sizeof(ExpandSmem<BN, NT>), e->stream>>>(D, e->eye2);
         e->launches++;
     } else if (e->puct_defer) {
@@ -917,6 +923,13 @@ extern "C" int tg_collect(tg_engine* e, tg_step_result* out)
         long long h[16];
         CK(cudaMemcpy(h, D.prof, sizeof h, cudaMemcpyDeviceToHost));
         CK(cudaMemset(D.prof, 0, 64 * sizeof(long long)));
+        if (e->puct_wave) {
+            const double st = (double)std::max(1ll, h[5]), g0 = (double)std::max(1ll, h[6]);
+            fprintf(stderr, "wavefront walk (game 0): prologue %lld cycles, %lld steps, descents in flight per step %.2f, cycles per step: scoring %.0f  leader %.0f  fetch %.0f"
+                            "  [group 0 when it scores (%lld steps): operands %.0f, + divisions %.0f, + warp argmax %.0f; after B1: fold %.0f, + leader updates %.0f]\n",
+                    h[0], h[5], (double)h[1] / st, (double)h[8] / st, (double)h[9] / st, (double)h[10] / st, h[6], (double)h[2] / g0, (double)h[3] / g0, (double)h[4] / g0,
+                    (double)h[7] / g0, (double)h[11] / g0);
+        }
         fprintf(stderr, "descend profile (game 0, cycles): copy %lld  select %lld (%lld)  put_stone %lld  expand %lld (%lld)  push_leaf %lld (%lld)"
                         "  [block kernels, select: scores %lld  argmax %lld  row wait %lld]  [warp put_stone: captures %lld (%lld cycles), passes %lld (%lld)]\n",
                 h[0], h[1], h[5], h[2], h[3], h[6], h[4], h[7], h[8], h[9], h[10], h[12], h[13], h[14], h[15]);
