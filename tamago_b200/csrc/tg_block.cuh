@@ -854,10 +854,10 @@ __global__ void __launch_bounds__(NT) k_walk_puct_blk(Dev D, const uint32_t* __r
                 int victim = 1;
                 if (nc > 2) { victim = rr; if (victim == slot) victim = victim + 1 < nc ? victim + 1 : 1; rr = victim + 1 < nc ? victim + 1 : 1; }
                 stage_node<N, NT>(slot_ptr(victim), t, ci, k);
-                if (k.tid == 0) ws.tag[victim] = ci;
                 stage_wait();
                 k.sync();
-                hit = victim;
+                if (k.tid == 0) ws.tag[victim] = ci;         // (after the barrier: slower threads may still be in the lookup above;
+                hit = victim;                                //  the next lookup is behind the barriers of the next selection)
                 if (prof) { const long long cc = clock64(); D.prof[10] += cc - pt0; pt0 = cc; }
             }
             cur = ci; slot = hit;
@@ -991,33 +991,31 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
             constexpr int CHG = (G::A + GT - 1) / GT;
             double vv[CHG];
             int cvs[CHG];
-            bool redo = false, anyv = false;                 // redo: an operand outside the fast division's range (a prior below 2^-120)
+            bool redo = false;                               // redo: an operand outside the fast division's range (a prior below 2^-120)
 #pragma unroll
             for (int c = 0; c < CHG; c++) {
                 const int i = gt + c * GT;
                 const bool valid = i < nk;
                 cvs[c] = valid ? st.vis[i] + st.vl[i] : 0;
                 vv[c] = dmul(valid ? st.pol[i] : 0.0, sq);   // (1.0 * prior) * sqrt(...): the first product is exact
-                anyv |= cvs[c] != 0;
             }
             if (prof) { const long long c = clock64(); pr[2] += c - pt0; pr[6]++; }
-            if (__any_sync(0xffffffffu, anyv)) {
-                // all divisions of the thread's children as ONE straight-line block (ddiv_fast has no branch): 2 * CHG
-                // independent ~250-cycle chains that the scheduler interleaves
+            // divisions only where a warp has a visited child (below the root most warps have none): the walk is bound by
+            // instruction issue (16 warps on 4 schedulers), not by the latency of the division chains
 #pragma unroll
-                for (int c = 0; c < CHG; c++) {
-                    const int i = gt + c * GT;
-                    const bool has = cvs[c] != 0;
-                    const float vs = has ? st.vsum[i] : 0.f;
-                    const double num = vv[c];
-                    const bool hq = has && vs != 0.0f;       // 0 / x = +0 exactly: no division
-                    const bool hu = has && num != 0.0;
-                    bool sq_, su_;
-                    const double qd = ddiv_fast(hq ? (double)vs : 1.0, has ? (double)cvs[c] : 1.0, sq_);
-                    const double ud = ddiv_fast(hu ? num : 1.0, (double)(cvs[c] + 1), su_);
-                    if (has) vv[c] = dadd(hq ? qd : 0.0, hu ? ud : 0.0);
-                    redo |= (hq && sq_) || (hu && su_);
-                }
+            for (int c = 0; c < CHG; c++) {
+                const bool has = cvs[c] != 0;
+                if (!__any_sync(0xffffffffu, has)) continue;
+                const int i = gt + c * GT;
+                const float vs = has ? st.vsum[i] : 0.f;
+                const double num = vv[c];
+                const bool hq = has && vs != 0.0f;           // 0 / x = +0 exactly: no division
+                const bool hu = has && num != 0.0;
+                bool sq_, su_;
+                const double qd = ddiv_fast(hq ? (double)vs : 1.0, has ? (double)cvs[c] : 1.0, sq_);
+                const double ud = ddiv_fast(hu ? num : 1.0, (double)(cvs[c] + 1), su_);
+                if (has) vv[c] = dadd(hq ? qd : 0.0, hu ? ud : 0.0);
+                redo |= (hq && sq_) || (hu && su_);
             }
             if (cgos && nk >= 1 && (nk - 1) % GT == gt) {
 #pragma unroll

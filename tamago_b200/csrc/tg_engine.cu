@@ -75,7 +75,6 @@ struct tg_engine {
     bool puct_defer = false;                     // block-per-game batches: selections in one kernel, board work of all leaves in another
     int walk_slots = 2;                          // node-row cache slots of k_walk_puct_blk
     bool puct_wave = false;                      // deferred mode: the tree walk runs as a wavefront (k_wave_puct_blk)
-    int wave_nt = 512;                           // CTA size of the wavefront walk when the other block kernels use 512 threads
     int wave_gt = 128;                           // threads per descent of the wavefront walk (512-thread CTAs: 128 measured faster than 64)
     const uint32_t* eye2 = nullptr;              // eye table packed to two bits per code (block-per-game kernels keep it in shared memory)
 };
@@ -178,7 +177,7 @@ template <int BN> static int setup_blk_attr()
     CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_walk_puct_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (setup_wave_attr<BN, 1024, 128>() || setup_wave_attr<BN, 512, 64>() || setup_wave_attr<BN, 512, 128>() || setup_wave_attr<BN, 256, 64>() || setup_wave_attr<BN, 128, 32>()) return -1;
+    if ( setup_wave_attr<BN, 512, 64>() || setup_wave_attr<BN, 512, 128>() || setup_wave_attr<BN, 256, 64>() || setup_wave_attr<BN, 128, 32>()) return -1;
     CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 128>)));
     CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 256>)));
     CK(cudaFuncSetAttribute(k_expand_leaves_blk<BN, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpandSmem<BN, 512>)));
@@ -361,7 +360,6 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     // sequential walk); TG_PUCT_WAVE=0/1, TG_WAVE_GT=64/128 (512-thread CTAs) for A/B measurements
     e->puct_wave = e->puct_defer && !e->cfg.dedup;
     if (const char* wv = getenv("TG_PUCT_WAVE")) e->puct_wave = e->puct_defer && !e->cfg.dedup && atoi(wv) != 0;
-    if (const char* wn = getenv("TG_WAVE_NT")) e->wave_nt = atoi(wn) == 1024 ? 1024 : 512;
     if (const char* gt = getenv("TG_WAVE_GT")) e->wave_gt = atoi(gt) == 64 ? 64 : 128;
     e->walk_slots = games <= e->sms ? 12 : 2;
     if (const char* ws = getenv("TG_WALK_SLOTS")) e->walk_slots = std::min(16, std::max(2, atoi(ws)));
@@ -814,9 +812,7 @@ template <int BN, int NT> static int puct_iter_blk(tg_engine* e, int visits, int
     const Dev& D = e->D;
     if (e->puct_defer && e->puct_wave) {
         const int nsq = std::min(WAVE_SQRT_MAX, visits + batch + 2);              // sqrt table: visits + virtual losses + 1 of any node
-        if (NT == 512 && e->wave_gt == 128 && e->wave_nt == 1024)     // eight descents in flight, 128 threads each
-            k_wave_puct_blk<BN, 1024, 128><<<D.games, 1024, wave_smem<BN, 1024, 128>(nsq), e->stream>>>(D, e->eye2, visits, batch, strict, nsq);
-        else if (NT == 512 && e->wave_gt == 128)
+        if (NT == 512 && e->wave_gt == 128)
             k_wave_puct_blk<BN, NT, (NT == 512 ? 128 : NT / 4)><<<D.games, NT, wave_smem<BN, NT, (NT == 512 ? 128 : NT / 4)>(nsq), e->stream>>>(D, e->eye2, visits, batch, strict, nsq);
         else
             k_wave_puct_blk<BN, NT, (NT == 512 ? 64 : NT / 4)><<<D.games, NT, wave_smem<BN, NT, (NT == 512 ? 64 : NT / 4)>(nsq), e->stream>>>(D, e->eye2, visits, batch, strict, nsq);
