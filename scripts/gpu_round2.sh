@@ -17,6 +17,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
 timeout 900 ncu --set full --clock-control none -k regex:k_dualnet_tc -s 3 -c 2 -o gpurun_out/r02_prof_dualnet_tc -f python scripts/one_config.py c2 1 > gpurun_out/r02_ncu_dualnet_run.log 2>&1; echo "ncu dualnet exit $?"
 timeout 900 ncu --set full --clock-control none -k regex:k_dualnet_tc -s 3 -c 1 -o gpurun_out/r02_prof_dualnet_tc_19x19 -f python scripts/one_config.py sh19 1 > gpurun_out/r02_ncu_dualnet19_run.log 2>&1; echo "ncu dualnet19 exit $?"
 timeout 900 ncu --set full --clock-control none -k "regex:k_planes|k_backup|k_descend_sh|k_move_end|k_root_begin" -s 10 -c 8 -o gpurun_out/r02_prof_search_kernels -f python scripts/one_config.py c2 1 > gpurun_out/r02_ncu_search_run.log 2>&1; echo "ncu search exit $?"
-timeout 900 ncu --set full --clock-control none -k "regex:k_descend_puct_blk|k_backup_blk" -s 4 -c 4 -o gpurun_out/r02_prof_puct_block -f python scripts/one_config.py c5 1 > gpurun_out/r02_ncu_puct_run.log 2>&1; echo "ncu puct exit $?"
+timeout 900 ncu --set full --clock-control none -k "regex:k_wave_puct_blk|k_expand_leaves_blk|k_backup_blk|k_backup_priors_blk" -s 4 -c 8 -o gpurun_out/r02_prof_puct_block -f python scripts/one_config.py c5 1 > gpurun_out/r02_ncu_puct_run.log 2>&1; echo "ncu puct exit $?"
 python scripts/ncu_box_summary.py r02
 du -sh gpurun_out
