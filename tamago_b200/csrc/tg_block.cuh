@@ -1054,11 +1054,18 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
         if (prof) { const long long c = clock64(); pr[8] += c - pt0; pt0 = c; pr[5]++; }
         // ---- S2: the group leader applies the ply
         if (run) {
-            u64 k2 = k.lane < GW ? ws.px[gi][k.lane] : 0ull;
-            int next = k.lane < GW ? ws.pi[gi][k.lane] : INF;
-            warp_argmax_key(k2, next);
-            if (prof) pr[7] += clock64() - pt0;
             if (gt == 0) {
+                // only the leader needs the group's choice: it folds the GW per-warp partials itself (a handful of compares
+                // instead of three dependent warp reductions in every warp of the group)
+                u64 k2 = ws.px[gi][0];
+                int next = ws.pi[gi][0];
+#pragma unroll
+                for (int w = 1; w < GW; w++) {
+                    const u64 kw = ws.px[gi][w];
+                    const int iw = ws.pi[gi][w];
+                    if (kw > k2 || (kw == k2 && kw != 0ull && iw < next)) { k2 = kw; next = iw; }
+                }
+                if (prof) pr[7] += clock64() - pt0;
                 typename WS::GState& ms = ws.gst[gi];
                 if (fresh) ms = me;
                 const int cur = me.cur;
