@@ -145,6 +145,7 @@ template <int BN> static int setup_kernel_attrs()
     CK(cudaFuncSetAttribute(k_root_begin<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_descend_sh<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 4 * Geo<BN>::CP * 8));
+    CK(cudaFuncSetAttribute(k_descend_puct_snap<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 4 * Geo<BN>::CP * 8));
     CK(cudaFuncSetAttribute(k_move_end<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_reset<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_play<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -155,6 +156,7 @@ template <int BN> static int setup_kernel_attrs()
     CK(cudaFuncSetAttribute(k_root_begin<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_descend_sh<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_descend_puct_snap<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return 0;
 }
 constexpr int WAVE_SQRT_MAX = 4096;             // entries of the wavefront walk's square-root table (larger arguments are computed)
@@ -349,6 +351,14 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     // does not (latency): BASELINE configs[3] (1024 games) runs warp-per-game, configs[4] (one game) block-per-game
     e->puct_warp = getenv("TG_PUCT_WARP") != nullptr || (games > 3 * e->sms && getenv("TG_PUCT_BLOCK") == nullptr);
     e->unfused_planes = getenv("TG_UNFUSED_PLANES") != nullptr;
+    // board snapshots along the previous path for the one-descent-per-launch PUCT kernel (warp-per-game pools with batch 1:
+    // BASELINE configs[3]); up to 32 levels (256 plies) per game within 512 MB, none otherwise
+    D.snap_levels = 0; D.snap_words = e->CP * 7 / 4 + BLOOM_WORDS + 8;
+    if (e->puct_warp && e->cfg.batch_size == 1 && getenv("TG_PUCT_NOSNAP") == nullptr) {
+        const size_t per_level = (size_t)games * D.snap_words * 4;
+        D.snap_levels = (int)std::min<size_t>(32, ((size_t)512 << 20) / per_level);
+        if (D.snap_levels > 0 && (rc = dalloc(e, &D.snapb, (size_t)games * D.snap_levels * D.snap_words, false)) != 0) return bail(rc);
+    }
     e->puct_nt = games <= e->sms ? 512 : 256;
     if (const char* nt = getenv("TG_PUCT_NT")) e->puct_nt = atoi(nt);
     // few games and real batches: the board work of a batch's leaves is spread over the idle SMs (tg_block.cuh, deferred
@@ -871,7 +881,10 @@ extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int3
                 const int iters = (visits + batch - 1) / batch + 1;
                 for (int it = 0; it < iters && !rc; it++) {
                     if (e->puct_warp) {                  // warp-per-game kernels (TG_PUCT_WARP=1: A/B measurements)
-                        k_descend_puct<BN><<<grid, thr, sm + 4 * Geo<BN>::CP * 8, e->stream>>>(D, visits, batch, strict);
+                        if (batch == 1 && D.snap_levels > 0)
+                            k_descend_puct_snap<BN><<<grid, thr, sm + 4 * Geo<BN>::CP * 8, e->stream>>>(D, visits, strict);
+                        else
+                            k_descend_puct<BN><<<grid, thr, sm + 4 * Geo<BN>::CP * 8, e->stream>>>(D, visits, batch, strict);
                         rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
                         k_backup<BN><<<grid, thr, 0, e->stream>>>(D, 0);
                     } else {                             // block-per-game (tg_block.cuh): a ply runs puct_nt threads wide

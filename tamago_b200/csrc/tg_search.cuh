@@ -22,7 +22,7 @@ enum : int {
     GS_NLEAF = 20, GS_NUNIQ = 21, GS_SLOT0 = 22, GS_ERROR = 23, GS_DONE = 24, GS_DESC = 25,
     GS_PASSCNT = 26, GS_NMOVES = 27, GS_FINISHED = 28, GS_NEVER_RESIGN = 29, GS_LAST_MOVE = 30,
     GS_ROOT_K = 31, GS_ACTIVE = 32, GS_WINNER = 33, GS_RESIGNED = 34, GS_SCORE = 35, GS_ROOTPASS = 36,
-    GS_LAST_COLOR = 37, GS_EVALS = 38, GS_UEVALS = 39, GS_STRIDE = 48
+    GS_LAST_COLOR = 37, GS_EVALS = 38, GS_UEVALS = 39, GS_PREVLEN = 40, GS_SNAPLV = 41, GS_STRIDE = 48
 };
 enum : int { ERR_DEPTH = 1, ERR_HISTORY = 2, ERR_NODES = 4, ERR_QUEUE = 8 };
 enum : int { MODE_SH = 0, MODE_PUCT = 1 };
@@ -69,6 +69,9 @@ struct Dev {
     // constants
     const u64* zob; const uint8_t* eye;
     long long* prof;         // optional clock64 accumulators of game 0 (development: TG_PROF=1)
+    // board snapshots along the previous descent's path (k_descend_puct_snap): level l = the board after (l + 1) * SNAP_K plies
+    uint32_t* snapb;         // [games][snap_levels][snap_words]
+    int snap_levels, snap_words;
 };
 
 template <int N> struct WarpSmem {
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_root_begin(Dev D)
     if (lane == 0) {
         gs[GS_NNODES] = 0; gs[GS_PHASE] = 0; gs[GS_NPHASES] = 0; gs[GS_DONE] = 0; gs[GS_DESC] = 0; gs[GS_ROOTPASS] = 0;
         gs[GS_ERROR] = 0; gs[GS_EVALS] = 0; gs[GS_UEVALS] = 0;
+        gs[GS_PREVLEN] = 0; gs[GS_SNAPLV] = 0;               // board snapshots of k_descend_puct_snap belong to the old root
     }
     __syncwarp();
     const int color = gs[GS_COLOR];
@@ -430,6 +434,178 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
         __syncwarp();
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// One descent per launch (PUCT with batch 1, BASELINE configs[3]) WITHOUT replaying the whole path on the board.
+//   With one evaluation per descent nothing carries a virtual loss between descents, so consecutive descents of a game
+//   share almost their entire path (with a random-init net the tree is a ~100-ply chain: the previous path plus one ply),
+//   and k_descend_puct spends more than half of its time re-playing those same ~100 stones (put_stone: 4 k cycles per ply
+//   on a crowded 19x19 board).  Here the descent first walks the tree alone -- selections need no board -- and compares its
+//   path with the previous one; then it restores the deepest board snapshot that lies on the shared prefix (one snapshot
+//   every SNAP_K plies of the previous path, kept in HBM/L2), replays only the plies behind it (saving the snapshots it
+//   passes), and expands the leaf.  Same tree, same boards, same record entries as k_descend_puct (bit-identical results).
+constexpr int SNAP_K = 8;
+
+template <int N> __device__ __forceinline__ void snap_store(uint32_t* dst, const WBoard<N>& b, const BScal& s, int lane)
+{
+    constexpr int W = (int)(sizeof(WBoard<N>) / 4);
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&b);
+    for (int i = lane; i < W; i += 32) dst[i] = a[i];
+    if (lane == 0) {
+        dst[W] = (uint32_t)s.hash; dst[W + 1] = (uint32_t)(s.hash >> 32); dst[W + 2] = (uint32_t)s.moves; dst[W + 3] = (uint32_t)s.ko_pos;
+        dst[W + 4] = (uint32_t)s.ko_move; dst[W + 5] = (uint32_t)s.pris0; dst[W + 6] = (uint32_t)s.pris1;
+    }
+}
+template <int N> __device__ __forceinline__ void snap_load(WBoard<N>& b, BScal& s, const uint32_t* src, int lane)
+{
+    constexpr int W = (int)(sizeof(WBoard<N>) / 4);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&b);
+    for (int i = lane; i < W; i += 32) d[i] = src[i];
+    s.hash = (u64)src[W] | ((u64)src[W + 1] << 32); s.moves = (int)src[W + 2]; s.ko_pos = (int)src[W + 3];
+    s.ko_move = (int)src[W + 4]; s.pris0 = (int)src[W + 5]; s.pris1 = (int)src[W + 6];
+    __syncwarp();
+}
+
+template <int N>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct_snap(Dev D, int visits, int strict)
+{
+    using G = Geo<N>;
+    static_assert(sizeof(WBoard<N>) == 7 * G::CP + 4 * BLOOM_WORDS, "snapshot stride (tg_engine.cu: snap_words)");
+    constexpr int PMAX = G::AP * 2;                          // path entries kept in shared memory (the s1 scratch, 8 bytes per child)
+    const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
+    extern __shared__ __align__(16) unsigned char smem_raw_[];
+    u64* zs = reinterpret_cast<u64*>(smem_raw_ + sizeof(WarpSmem<N>) * SEARCH_WARPS);
+    for (int i = threadIdx.x; i < 4 * G::CELLS; i += SEARCH_WARPS * 32) zs[i] = D.zob[i];
+    __syncthreads();
+    if (g >= D.games) return;
+    int* gs = D.gs + (size_t)g * GS_STRIDE;
+    if (lane == 0) { gs[GS_NLEAF] = 0; gs[GS_NUNIQ] = 0; }
+    __syncwarp();
+    if (!gs[GS_ACTIVE] || gs[GS_FINISHED] || gs[GS_ERROR] || gs[GS_DONE]) return;
+    WarpSmem<N>& sm = warp_smem<N>();
+    const SelStage stage = { sm.s0, reinterpret_cast<int*>(&sm.an), reinterpret_cast<int*>(&sm.an) + G::AP,
+                             reinterpret_cast<float*>(&sm.an) + 2 * G::AP, reinterpret_cast<int*>(&sm.an) + 3 * G::AP,
+                             reinterpret_cast<int16_t*>(reinterpret_cast<int*>(&sm.an) + 4 * G::AP), sm.sthdr };
+    unsigned* spath = reinterpret_cast<unsigned*>(sm.s1);    // previous path, overwritten ply by ply with the new one
+    const Tree t = tree_of<G::AP>(D.tree, g);
+    stage_node_warp<G::AP>(stage, t, 0, lane);
+    BScal rs;
+    {                                                        // (the root board itself is only loaded if no snapshot can be used)
+        const int* sc = D.b_scal + (size_t)g * 8;
+        rs.hash = D.b_hash[g];
+        rs.moves = sc[0]; rs.ko_pos = sc[1]; rs.ko_move = sc[2]; rs.pris0 = sc[3]; rs.pris1 = sc[4];
+    }
+    const int root_color = gs[GS_COLOR];
+    u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
+    int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
+    const unsigned move_key = (unsigned)rs.moves;
+    unsigned* path = D.path + (size_t)g * D.cap * D.max_depth;                   // (queue entry 0: one leaf per launch)
+    const int prevlen = min(gs[GS_PREVLEN], PMAX), snaplv = gs[GS_SNAPLV];
+    for (int i = lane; i < prevlen; i += 32) spath[i] = path[i];
+    const int desc = gs[GS_DESC];
+    if (desc >= visits) { if (lane == 0) gs[GS_DONE] = 1; __syncwarp(); asm volatile("cp.async.wait_all;" ::: "memory"); return; }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    if (desc > 0) {                                          // is_move_decided (time_manager.py:146-163), as k_descend_puct
+        const int k = stage.hdr[H_K];
+        int top1 = 0;
+        for (int i = lane; i < k; i += 32) top1 = max(top1, stage.vis[i]);
+        top1 = warp_max_i(top1);
+        int nmax = 0, top2 = 0;
+        for (int i = lane; i < k; i += 32) { const int v = stage.vis[i]; if (v == top1) nmax++; else top2 = max(top2, v); }
+        nmax = warp_sum_i(nmax); top2 = warp_max_i(top2);
+        if (nmax >= 2) top2 = top1;
+        const int remaining = visits - stage.hdr[H_NV];
+        const int cutoff = strict ? 0 : top1 - top2;
+        if (remaining < cutoff) { if (lane == 0) gs[GS_DONE] = 1; __syncwarp(); return; }
+    }
+    const bool prof = D.prof && g == 0 && lane == 0;
+    long long pt0 = prof ? clock64() : 0;
+    // ---- the walk (tree.py:213-241 without the board).  The rows of the next node are fetched after the selection that leads
+    // to it and waited for (≈ 3 k cycles per ply at 19x19: what put_stone used to hide).  Fetching the node the previous path
+    // visited at the next depth DURING the selection was measured slower (select 3.0 k -> 7.0 k cycles per ply, step 315 -> 343 ms).
+    int cur = 0, plen = 0, shared = 0, m1 = (rs.moves >= 1 && rs.moves - 1 < G::MAXREC) ? hp[rs.moves - 1] : -1;
+    int ci = NOT_EXPANDED, next = 0;
+    size_t row = 0;
+    for (;;) {
+        next = select_puct(stage, D.cgos != 0, lane);
+        if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
+        row = (size_t)cur * G::AP;
+        const int mv = stage.action[next];
+        const int cv_before = stage.vis[next] + stage.vl[next];
+        ci = stage.cidx[next];
+        const int vl_node = stage.hdr[H_VL], vl_edge = stage.vl[next];
+        const unsigned entry = ((unsigned)cur << PATH_NODE_SHIFT) | (unsigned)next;
+        const bool same = shared == plen && plen < prevlen && spath[plen] == entry;
+        __syncwarp();                                        // every lane has read the staged node and the old path entry
+        if (same) shared++;
+        const bool spec = ci != NOT_EXPANDED && cv_before >= 1;
+        if (spec) stage_node_warp<G::AP>(stage, t, ci, lane);
+        if (lane == 0) {
+            path[plen] = entry;
+            if (plen < PMAX) spath[plen] = entry;
+            t.hdr[(size_t)cur * H_STRIDE + H_VL] = vl_node + 1; t.cvl[row + next] = vl_edge + 1;           // :221 add_virtual_loss
+        }
+        plen++;
+        const int moves = rs.moves + plen;
+        int expand_threshold = 1;
+        if (moves > 2) {                                     // :224-229
+            if (moves - 1 >= G::MAXREC) { asm volatile("cp.async.wait_all;" ::: "memory"); if (lane == 0) gs[GS_ERROR] |= ERR_HISTORY; __syncwarp(); return; }
+            if (mv == PASS && m1 == PASS) expand_threshold = 10000000;
+        }
+        m1 = mv;
+        if (cv_before + 1 < expand_threshold + 1) {          // :231-241: this edge ends the descent
+            if (spec) { asm volatile("cp.async.wait_all;" ::: "memory"); }
+            break;
+        }
+        cur = ci;
+        if (plen >= D.max_depth) { asm volatile("cp.async.wait_all;" ::: "memory"); if (lane == 0) gs[GS_ERROR] |= ERR_DEPTH; __syncwarp(); return; }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (prof) { const long long c = clock64(); D.prof[10] += c - pt0; pt0 = c; }
+    }
+    __syncwarp();
+    // ---- the board at the leaf: deepest snapshot on the shared prefix, then the plies behind it
+    const int want = min(min(shared / SNAP_K, snaplv), D.snap_levels);
+    uint32_t* snaps = D.snapb + (size_t)g * D.snap_levels * D.snap_words;
+    BScal s = rs;
+    if (want == 0) wb_load<N>(sm.scratch, s, pool_of<N>(D), g, lane);            // tree.py:147 (straight from the root pool)
+    else snap_load<N>(sm.scratch, s, snaps + (size_t)(want - 1) * D.snap_words, lane);
+    if (prof) { const long long c = clock64(); D.prof[0] += c - pt0; pt0 = c; }
+    for (int d0 = want * SNAP_K; d0 < plen; d0 += 32) {
+        const int dl = d0 + lane;
+        int mvl = 0;
+        if (dl < plen) {
+            const unsigned e = dl < PMAX ? spath[dl] : path[dl];
+            mvl = t.action[(size_t)(e >> PATH_NODE_SHIFT) * G::AP + (e & ((1u << PATH_NODE_SHIFT) - 1))];
+        }
+        const int n = min(32, plen - d0);
+        for (int i = 0; i < n; i++) {
+            const int d = d0 + i;
+            const int mv = __shfl_sync(0xffffffffu, mvl, i);
+            wb_put_stone<N>(sm.scratch, s, mv, (d & 1) ? opp(root_color) : root_color, zs, hh, hp, lane);   // :217
+            const int lv = (d + 1) / SNAP_K;
+            if ((d + 1) % SNAP_K == 0 && lv <= D.snap_levels) { __syncwarp(); snap_store<N>(snaps + (size_t)(lv - 1) * D.snap_words, sm.scratch, s, lane); }
+        }
+    }
+    if (prof) { const long long c = clock64(); D.prof[2] += c - pt0; pt0 = c; }
+    const int color = (plen & 1) ? opp(root_color) : root_color;                 // to move at the leaf
+    if (ci == NOT_EXPANDED) {
+        ci = expand_node<N>(D, t, g, gs, sm.scratch, sm.an, s, color, hh, move_key, lane);
+        if (prof) { const long long c = clock64(); D.prof[3] += c - pt0; pt0 = c; D.prof[6]++; }
+        if (ci < 0) return;
+        if (lane == 0) t.cidx[row + next] = ci;
+        __threadfence_block();
+        __syncwarp();
+    }
+    push_leaf<N>(D, g, gs, sm.scratch, s, color, path, plen, ci, lane, -1, true);
+    if (prof) { const long long c = clock64(); D.prof[4] += c - pt0; D.prof[7]++; }
+    __syncwarp();
+    if (lane == 0) {
+        gs[GS_DESC] = desc + 1;
+        gs[GS_PREVLEN] = plen;
+        gs[GS_SNAPLV] = min(D.snap_levels, plen / SNAP_K);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -76,10 +76,16 @@ __device__ __forceinline__ void stage_node_warp(const SelStage& st, const Tree& 
 
 // node.py:141-157 + pucb.py:8-29 on a staged node.  Returns the child index (warp-uniform); the float64 arithmetic runs in
 // the reference's order (lowest index first on ties).
+__device__ inline int select_puct_ready(const SelStage& st, bool cgos, int lane);
 __device__ inline int select_puct(const SelStage& st, bool cgos, int lane)
 {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
+    return select_puct_ready(st, cgos, lane);
+}
+// (the staged rows are complete; other asynchronous copies of the warp may still be in flight)
+__device__ inline int select_puct_ready(const SelStage& st, bool cgos, int lane)
+{
     const int k = st.hdr[H_K];
     const double sq = sqrt((double)(st.hdr[H_NV] + st.hdr[H_VL] + 1));
     double bv = 0.0; int bi = 0x7fffffff;

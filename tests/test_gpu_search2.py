@@ -55,8 +55,8 @@ def _oracle_game(args):
     return r["pos"], r["winner"], r["is_resign"], r["score"]
 
 
-@pytest.mark.parametrize("batch", [1, 8])
-def test_c4_full_games_19x19_puct400_vs_oracle(batch):
+@pytest.mark.parametrize("batch,warp", [(1, False), (8, False), (1, True)])
+def test_c4_full_games_19x19_puct400_vs_oracle(batch, warp, monkeypatch):
     """BASELINE configs[3] played to the end: 8 whole 19x19 games, 400-visit PUCT + super-ko with the early stop of
     is_move_decided, every move / resignation / final score equal to the oracle's game (non-dyadic evaluator)."""
     import multiprocessing as mp
@@ -64,6 +64,8 @@ def test_c4_full_games_19x19_puct400_vs_oracle(batch):
     from oracle import oracle as orc
     orc.build()
     size, ng, visits, seed = 19, 8, 400, 41
+    if warp:                                             # the kernels configs[3] itself runs (1024 games): one warp per game, board snapshots
+        monkeypatch.setenv("TG_PUCT_WARP", "1")
     with mp.get_context("fork").Pool(min(ng, os.cpu_count() or 1)) as pool:
         fut = pool.map_async(_oracle_game, [(size, seed, g, visits, batch) for g in range(ng)])
         e = tb.Engine(board_size=size, games=ng, max_visits=visits, superko=True, batch_size=batch, evaluator=tb.EVAL_HASHNET2, seed=seed)
@@ -115,7 +117,7 @@ def test_puct_kernel_variants_agree(monkeypatch):
         boards.append((b, color)); mls.append(ml)
 
     def run(ng, batch, visits, dedup, warp, env=()):
-        for key in ("TG_PUCT_WARP", "TG_PUCT_DEFER", "TG_WALK_SLOTS", "TG_PUCT_WAVE", "TG_WAVE_GT"):
+        for key in ("TG_PUCT_WARP", "TG_PUCT_DEFER", "TG_WALK_SLOTS", "TG_PUCT_WAVE", "TG_WAVE_GT", "TG_PUCT_NOSNAP"):
             monkeypatch.delenv(key, raising=False)
         if warp:
             monkeypatch.setenv("TG_PUCT_WARP", "1")
@@ -138,6 +140,12 @@ def test_puct_kernel_variants_agree(monkeypatch):
 
     for batch, visits, dedup in ((1, 48, False), (16, 90, True), (16, 90, False)):
         ref = run(160, batch, visits, dedup, warp=True)
+        if batch == 1:                                   # warp kernels: board snapshots along the previous path (default) or full replays
+            alt = run(160, batch, visits, dedup, warp=True, env=(("TG_PUCT_NOSNAP", "1"),))
+            assert np.array_equal(alt[0]["move"], ref[0]["move"]) and np.array_equal(alt[0]["visits"], ref[0]["visits"]) and alt[2] == ref[2]
+            for a, b in zip(alt[1], ref[1]):
+                for key in ("children_visits", "children_value_sum", "children_policy", "children_index", "children_virtual_loss"):
+                    assert np.array_equal(a[key], b[key]), ("snapshots", key)
         # block kernels: 256 / 512 threads; batches > 1 on <= 148 games split into tree walk + deferred expansion by default,
         # forced on / off here, with the full node-row cache, a three-slot cache (evictions) and none
         # and the walk either pipelined over the descents (wavefront; not with leaf deduplication) or sequential
