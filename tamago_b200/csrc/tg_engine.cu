@@ -128,6 +128,7 @@ static void build_eye_table(std::vector<uint8_t>& eye)
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int PUCT_SQRT_MAX = 1024;             // entries of the warp PUCT kernels' square-root table (larger arguments are computed)
 static size_t search_smem(int N)
 {
     switch (N) { case 9: return sizeof(WarpSmem<9>) * SEARCH_WARPS; case 13: return sizeof(WarpSmem<13>) * SEARCH_WARPS;
@@ -144,8 +145,8 @@ template <int BN> static int setup_kernel_attrs()
     const int bytes = (int)(sizeof(WarpSmem<BN>) * SEARCH_WARPS);
     CK(cudaFuncSetAttribute(k_root_begin<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_descend_sh<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 4 * Geo<BN>::CP * 8));
-    CK(cudaFuncSetAttribute(k_descend_puct_snap<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 4 * Geo<BN>::CP * 8));
+    CK(cudaFuncSetAttribute(k_descend_puct<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 4 * Geo<BN>::CP * 8 + PUCT_SQRT_MAX * 8));
+    CK(cudaFuncSetAttribute(k_descend_puct_snap<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 4 * Geo<BN>::CP * 8 + PUCT_SQRT_MAX * 8));
     CK(cudaFuncSetAttribute(k_move_end<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_reset<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_play<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -881,10 +882,11 @@ extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int3
                 const int iters = (visits + batch - 1) / batch + 1;
                 for (int it = 0; it < iters && !rc; it++) {
                     if (e->puct_warp) {                  // warp-per-game kernels (TG_PUCT_WARP=1: A/B measurements)
+                        const int nsq = std::min(PUCT_SQRT_MAX, visits + batch + 2);   // sqrt(visits + virtual losses + 1) table
                         if (batch == 1 && D.snap_levels > 0)
-                            k_descend_puct_snap<BN><<<grid, thr, sm + 4 * Geo<BN>::CP * 8, e->stream>>>(D, visits, strict);
+                            k_descend_puct_snap<BN><<<grid, thr, sm + 4 * Geo<BN>::CP * 8 + nsq * 8, e->stream>>>(D, visits, strict, nsq);
                         else
-                            k_descend_puct<BN><<<grid, thr, sm + 4 * Geo<BN>::CP * 8, e->stream>>>(D, visits, batch, strict);
+                            k_descend_puct<BN><<<grid, thr, sm + 4 * Geo<BN>::CP * 8 + nsq * 8, e->stream>>>(D, visits, batch, strict, nsq);
                         rc = launch_eval<BN>(e, 0, (int)std::min<size_t>((size_t)games * batch, (size_t)e->slot_cap), iters <= 24 ? &ev : nullptr);
                         k_backup<BN><<<grid, thr, 0, e->stream>>>(D, 0);
                     } else {                             // block-per-game (tg_block.cuh): a ply runs puct_nt threads wide

@@ -322,14 +322,17 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_sh(Dev D)
 //   as soon as the node is known -- the root's at kernel start (under the board load) and at the end of a descent, a
 //   child's right after the selection that leads to it (under put_stone).
 template <int N>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int visits, int batch, int strict)
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int visits, int batch, int strict, int nsqrt)
 {
     using G = Geo<N>;
     const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
-    // the Zobrist keys (one read per put_stone, ~100 plies per descent) sit behind the per-warp scratch, shared by the CTA
+    // the Zobrist keys (one read per put_stone, ~100 plies per descent) sit behind the per-warp scratch, shared by the CTA,
+    // and behind them a table of sqrt(n) for the selections
     extern __shared__ __align__(16) unsigned char smem_raw_[];
     u64* zs = reinterpret_cast<u64*>(smem_raw_ + sizeof(WarpSmem<N>) * SEARCH_WARPS);
+    double* sqtab = reinterpret_cast<double*>(zs + 4 * G::CP);
     for (int i = threadIdx.x; i < 4 * G::CELLS; i += SEARCH_WARPS * 32) zs[i] = D.zob[i];
+    for (int i = threadIdx.x; i < nsqrt; i += SEARCH_WARPS * 32) sqtab[i] = sqrt((double)i);
     __syncthreads();
     if (g >= D.games) return;
     int* gs = D.gs + (size_t)g * GS_STRIDE;
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct(Dev D, int v
         unsigned* path = D.path + ((size_t)g * D.cap + gs[GS_NLEAF]) * D.max_depth;
         bool fail = false;
         for (;;) {
-            const int next = select_puct(stage, D.cgos != 0, lane);                     // :213
+            const int next = select_puct(stage, D.cgos != 0, lane, sqtab, nsqrt);       // :213
             if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
             const size_t row = (size_t)cur * G::AP;
             const int mv = stage.action[next];
@@ -467,7 +470,7 @@ template <int N> __device__ __forceinline__ void snap_load(WBoard<N>& b, BScal& 
 }
 
 template <int N>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct_snap(Dev D, int visits, int strict)
+__global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct_snap(Dev D, int visits, int strict, int nsqrt)
 {
     using G = Geo<N>;
     static_assert(sizeof(WBoard<N>) == 7 * G::CP + 4 * BLOOM_WORDS, "snapshot stride (tg_engine.cu: snap_words)");
@@ -475,7 +478,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct_snap(Dev D, 
     const int g = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5), lane = lane_id();
     extern __shared__ __align__(16) unsigned char smem_raw_[];
     u64* zs = reinterpret_cast<u64*>(smem_raw_ + sizeof(WarpSmem<N>) * SEARCH_WARPS);
+    double* sqtab = reinterpret_cast<double*>(zs + 4 * G::CP);
     for (int i = threadIdx.x; i < 4 * G::CELLS; i += SEARCH_WARPS * 32) zs[i] = D.zob[i];
+    for (int i = threadIdx.x; i < nsqrt; i += SEARCH_WARPS * 32) sqtab[i] = sqrt((double)i);
     __syncthreads();
     if (g >= D.games) return;
     int* gs = D.gs + (size_t)g * GS_STRIDE;
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) k_descend_puct_snap(Dev D, 
     int ci = NOT_EXPANDED, next = 0;
     size_t row = 0;
     for (;;) {
-        next = select_puct(stage, D.cgos != 0, lane);
+        next = select_puct(stage, D.cgos != 0, lane, sqtab, nsqrt);
         if (prof) { const long long c = clock64(); D.prof[1] += c - pt0; pt0 = c; D.prof[5]++; }
         row = (size_t)cur * G::AP;
         const int mv = stage.action[next];

@@ -76,18 +76,15 @@ __device__ __forceinline__ void stage_node_warp(const SelStage& st, const Tree& 
 
 // node.py:141-157 + pucb.py:8-29 on a staged node.  Returns the child index (warp-uniform); the float64 arithmetic runs in
 // the reference's order (lowest index first on ties).
-__device__ inline int select_puct_ready(const SelStage& st, bool cgos, int lane);
-__device__ inline int select_puct(const SelStage& st, bool cgos, int lane)
+// sqtab (optional): sqrt((double)n) for n < nsqrt in shared memory -- a float64 square root is a ~450-cycle dependent chain
+// that every lane would repeat at every ply.
+__device__ inline int select_puct(const SelStage& st, bool cgos, int lane, const double* sqtab = nullptr, int nsqrt = 0)
 {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    return select_puct_ready(st, cgos, lane);
-}
-// (the staged rows are complete; other asynchronous copies of the warp may still be in flight)
-__device__ inline int select_puct_ready(const SelStage& st, bool cgos, int lane)
-{
     const int k = st.hdr[H_K];
-    const double sq = sqrt((double)(st.hdr[H_NV] + st.hdr[H_VL] + 1));
+    const int nsq = st.hdr[H_NV] + st.hdr[H_VL] + 1;
+    const double sq = nsq < nsqrt ? sqtab[nsq] : sqrt((double)nsq);
     double bv = 0.0; int bi = 0x7fffffff;
     for (int i = lane; i < k; i += 32) {          // (unrolling for overlapping divisions was measured slower: 7.4 k -> 10.6 k cycles)
         const int cv = st.vis[i] + st.vl[i];
