@@ -928,13 +928,16 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
     const long long pk0 = prof ? clock64() : 0;
     const Tree t = tree_of<G::AP>(D.tree, g);
     stage_node<N, NT>(sm.st[0], t, 0, k);
-    for (int i = k.tid; i < 4096 / 4; i += NT) reinterpret_cast<uint4*>(sm.eye2)[i] = reinterpret_cast<const uint4*>(eye2)[i];
-    for (int i = k.tid; i < 4 * G::CELLS; i += NT) sm.zob[i] = D.zob[i];
     for (int i = k.tid; i < WALK_MAX_BATCH; i += NT) { ws.final_idx[i] = -1; ws.alloc[i] = 0; }
     if (k.tid < NG) { ws.gst[k.tid].active = 0; ws.gst[k.tid].wait_ci = -1; ws.gst[k.tid].ord = INF; ws.dec[k.tid] = -1; }
     if (k.tid == 0) ws.err = 0;
-    BScal rs;
-    bb_load<N, NT>(sm.root, rs, pool_of<N>(D), g, k);
+    BScal rs;                                                // the walk needs the root's scalars; its board, the eye table and the
+    {                                                        // Zobrist keys are loaded by the first on-demand materialisation, if any
+        const int* sc = D.b_scal + (size_t)g * 8;
+        rs.hash = D.b_hash[g];
+        rs.moves = sc[0]; rs.ko_pos = sc[1]; rs.ko_move = sc[2]; rs.pris0 = sc[3]; rs.pris1 = sc[4];
+    }
+    bool board_loaded = false;
     const int root_color = gs[GS_COLOR];
     u64* hh = D.hist_hash + (size_t)g * G::MAXREC;
     int16_t* hp = D.hist_pos + (size_t)g * G::MAXREC;
@@ -1149,6 +1152,13 @@ __global__ void __launch_bounds__(NT) k_wave_puct_blk(Dev D, const uint32_t* __r
             }
             k.sync();
             if (idx >= D.tree.max_nodes) { if (k.tid == 0) ws.err = ERR_NODES; k.sync(); break; }
+            if (!board_loaded) {
+                for (int i = k.tid; i < 4096 / 4; i += NT) reinterpret_cast<uint4*>(sm.eye2)[i] = reinterpret_cast<const uint4*>(eye2)[i];
+                for (int i = k.tid; i < 4 * G::CELLS; i += NT) sm.zob[i] = D.zob[i];
+                BScal tmp;
+                bb_load<N, NT>(sm.root, tmp, pool_of<N>(D), g, k);
+                board_loaded = true;
+            }
             bb_copy<N, NT>(sm.scratch, sm.root, k);
             BScal s = rs;
             int c = root_color;
