@@ -74,6 +74,7 @@ struct tg_engine {
     int puct_nt = 256;                           // threads per game of the block-per-game PUCT kernels (128, 256 or 512)
     bool puct_defer = false;                     // block-per-game batches: selections in one kernel, board work of all leaves in another
     int walk_slots = 2;                          // node-row cache slots of k_walk_puct_blk
+    int snap_plan = 0;                           // board-snapshot levels per game k_descend_puct_snap will get (0: none)
     bool puct_wave = false;                      // deferred mode: the tree walk runs as a wavefront (k_wave_puct_blk)
     int wave_gt = 128;                           // threads per descent of the wavefront walk (512-thread CTAs: 128 measured faster than 64)
     const uint32_t* eye2 = nullptr;              // eye table packed to two bits per code (block-per-game kernels keep it in shared memory)
@@ -354,12 +355,10 @@ extern "C" int tg_engine_create(const tg_config* cfg, tg_engine** out)
     e->unfused_planes = getenv("TG_UNFUSED_PLANES") != nullptr;
     // board snapshots along the previous path for the one-descent-per-launch PUCT kernel (warp-per-game pools with batch 1:
     // BASELINE configs[3]); up to 32 levels (256 plies) per game within 512 MB, none otherwise
-    D.snap_levels = 0; D.snap_words = e->CP * 7 / 4 + BLOOM_WORDS + 8;
-    if (e->puct_warp && e->cfg.batch_size == 1 && getenv("TG_PUCT_NOSNAP") == nullptr) {
-        const size_t per_level = (size_t)games * D.snap_words * 4;
-        D.snap_levels = (int)std::min<size_t>(32, ((size_t)512 << 20) / per_level);
-        if (D.snap_levels > 0 && (rc = dalloc(e, &D.snapb, (size_t)games * D.snap_levels * D.snap_words, false)) != 0) return bail(rc);
-    }
+    // (allocated by the first PUCT move: a pool that only ever runs sequential halving does not pay for them)
+    D.snap_levels = 0; D.snap_words = e->CP * 7 / 4 + BLOOM_WORDS + 8; e->snap_plan = 0;
+    if (e->puct_warp && e->cfg.batch_size == 1 && getenv("TG_PUCT_NOSNAP") == nullptr)
+        e->snap_plan = (int)std::min<size_t>(32, ((size_t)512 << 20) / ((size_t)games * D.snap_words * 4));
     e->puct_nt = games <= e->sms ? 512 : 256;
     if (const char* nt = getenv("TG_PUCT_NT")) e->puct_nt = atoi(nt);
     // few games and real batches: the board work of a batch's leaves is spread over the idle SMs (tg_block.cuh, deferred
@@ -856,6 +855,11 @@ extern "C" int tg_genmove_async(tg_engine* e, int32_t mode, int32_t visits, int3
     int rc = 0, ev = 2;
     Dev& D = e->D;
     if (mode == TG_MODE_SH) { D.cap = e->cap_sh; D.max_depth = e->depth_sh; } else { D.cap = e->cap_puct; D.max_depth = e->depth_puct; }
+    if (mode == TG_MODE_PUCT && e->snap_plan > 0 && D.snap_levels == 0) {        // first PUCT move of a warp-per-game pool
+        const int rc0 = dalloc(e, &D.snapb, (size_t)games * e->snap_plan * D.snap_words, false);
+        if (rc0) return rc0;
+        D.snap_levels = e->snap_plan;
+    }
     const int max_moves = 2 * e->NN;
     CK(cudaEventRecord(e->events[0], e->stream));
     DISPATCH_N(e, {
