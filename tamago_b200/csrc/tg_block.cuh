@@ -1407,11 +1407,17 @@ __global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit, int pri
             for (int d = lane; d < plen; d += 32) { e_key[o + d] = path[plen - 1 - d]; e_who[o + d] = ((unsigned)i << 16) | (unsigned)d; }
         }
         __syncthreads();
+        // A node sits at ONE depth of the tree, so in every leaf's segment it can only be at one position (its depth counted
+        // from the root end of the segment): both scans visit one entry per leaf instead of every entry of the batch.
         for (int e = tid; e < E; e += NT) {
             const unsigned key = e_key[e], node = key >> PATH_NODE_SHIFT;
+            const int i0 = (int)(e_who[e] >> 16);
+            const int depth = (s_off[i0 + 1] - s_off[i0]) - 1 - (int)(e_who[e] & 0xffffu);       // plies between the root and this edge
             bool seen_edge = false, seen_node = false;
-            for (int j = 0; j < e && !(seen_edge && seen_node); j++) {
-                const unsigned kj = e_key[j];
+            for (int i = 0; i < i0 && !(seen_edge && seen_node); i++) {
+                const int o = s_off[i], pl = s_off[i + 1] - o;
+                if (depth >= pl) continue;
+                const unsigned kj = e_key[o + pl - 1 - depth];
                 seen_node |= (kj >> PATH_NODE_SHIFT) == node;
                 seen_edge |= kj == key;
             }
@@ -1422,12 +1428,13 @@ __global__ void __launch_bounds__(NT) k_backup_blk(Dev D, int use_logit, int pri
             float es = seen_edge ? 0.f : t.cvsum[row + c];
             float hs = seen_node ? 0.f : __int_as_float(h[H_VSUM]);
             int ec = 0, hc = 0; bool has0 = false; float last0 = 0.f;
-            for (int j = e; j < E; j++) {
-                const unsigned kj = e_key[j];
+            for (int i = i0; i < nl; i++) {
+                const int o = s_off[i], pl = s_off[i + 1] - o;
+                if (depth >= pl) continue;
+                const int d = pl - 1 - depth;
+                const unsigned kj = e_key[o + d];
                 if ((kj >> PATH_NODE_SHIFT) != node) continue;
-                const unsigned who = e_who[j];
-                const int d = (int)(who & 0xffffu);
-                const float v0 = s_val[who >> 16];
+                const float v0 = s_val[i];
                 const float v1 = __fsub_rn(1.0f, v0);
                 const float val = d == 0 ? v0 : ((d & 1) ? v1 : __fsub_rn(1.0f, v1));                                 // value = 1 - value per ply (:313)
                 if (!seen_node) { hs = __fadd_rn(hs, val); hc++; }
